@@ -1,0 +1,79 @@
+"""Deterministic synthetic inputs for the utility loop.
+
+Everything is generated on the CPU from ``torch.Generator`` seeds so that the
+oracle (CPU) and the CUDA path see bit-identical inputs:
+
+* ``W0``      -- random-init ViT state_dict, N(0, 0.02) weights; biases and
+  LayerNorm parameters are *also* perturbed (HF's default zeros/ones would hide
+  bias / gain bugs in a parity test);
+* client ``j`` -- ``W0 + sigma * N(0, 1)`` per tensor;
+* ``n_j``     -- ``1000 * (j + 1)`` training samples, so FedAvg ratios differ;
+* val set     -- N(0,1) images, uniform labels, served as the dict samples
+  ``{'image', 'label', 'image_name'}`` the reference's ``evaluation`` expects
+  (reference ``federated_learning/utils.py:880``).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Tuple
+
+import torch
+
+from .layout import VitConfig, state_dict_spec
+
+
+def make_state_dict(cfg: VitConfig, seed: int = 0, std: float = 0.02) -> "OrderedDict[str, torch.Tensor]":
+    g = torch.Generator().manual_seed(1_000_003 * seed + 17)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for key, shape in state_dict_spec(cfg):
+        t = torch.randn(shape, generator=g, dtype=torch.float32) * std
+        if key.endswith("layernorm_before.weight") or key.endswith("layernorm_after.weight") \
+                or key == "vit.layernorm.weight":
+            t += 1.0
+        sd[key] = t
+    return sd
+
+
+def make_client_state_dict(w0: Dict[str, torch.Tensor], client: int, seed: int = 0,
+                           sigma: float = 0.02) -> "OrderedDict[str, torch.Tensor]":
+    g = torch.Generator().manual_seed(1_000_003 * seed + 7919 * (client + 1))
+    out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for key, t in w0.items():
+        out[key] = t + sigma * torch.randn(t.shape, generator=g, dtype=torch.float32)
+    return out
+
+
+def client_sizes(n_clients: int) -> List[int]:
+    return [1000 * (j + 1) for j in range(n_clients)]
+
+
+def make_val_set(cfg: VitConfig, n: int, seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    g = torch.Generator().manual_seed(1_000_003 * seed + 424_243)
+    images = torch.randn((n, cfg.channels, cfg.image, cfg.image), generator=g, dtype=torch.float32)
+    labels = torch.randint(0, cfg.n_cls, (n,), generator=g, dtype=torch.int64)
+    return images, labels
+
+
+class DictSampleDataset(torch.utils.data.Dataset):
+    """Dataset yielding the reference's sample dicts."""
+
+    def __init__(self, images: torch.Tensor, labels: torch.Tensor):
+        assert images.shape[0] == labels.shape[0]
+        self.images, self.labels = images, labels
+
+    def __len__(self) -> int:
+        return self.images.shape[0]
+
+    def __getitem__(self, i: int):
+        return {"image": self.images[i], "label": self.labels[i], "image_name": f"synthetic_{i:06d}"}
+
+
+class SizedStub:
+    """Stands in for a client's training set: only ``len()`` is ever read
+    (reference ``federated_learning/client2.py:14-15``)."""
+
+    def __init__(self, n: int):
+        self._n = int(n)
+
+    def __len__(self) -> int:
+        return self._n
