@@ -1,0 +1,173 @@
+/*
+ * svit.h -- C ABI of libsvit.so: the B200 (sm_100a) kernels behind the
+ * client-contribution utility loop of shapley-vit.
+ *
+ * The reference (juniarto-samsudin/shapley-vit) is pure Python/PyTorch and has
+ * no FFI of its own; the entry points below are what a binding for its hot path
+ * replaces, function by function (paths relative to the reference root):
+ *
+ *   svit_aggregate        <- get_aggregated_model      federated_learning/utils.py:781-792
+ *                            + ServerBase.model_agg_lazy federated_learning/server2.py:121-127
+ *                            (FedAvg ratios from ServerBase.get_agg_ratio, server2.py:68-81)
+ *   svit_patchify,
+ *   svit_forward_batched  <- net(img).logits inside evaluation, federated_learning/utils.py:886
+ *                            (HF ViTForImageClassification built at start.py:258-267)
+ *   svit_score            <- argmax / correct / CrossEntropy(sum) in evaluation,
+ *                            federated_learning/utils.py:891-894
+ *   svit_gemm, svit_layernorm, svit_attention
+ *                         <- the ATen/cuBLAS calls the HF forward issues per layer; exported so
+ *                            each kernel can be parity-tested and timed in isolation
+ *   svit_layout_*         <- the state_dict key order the reference iterates
+ *                            (federated_learning/utils.py:745-748, 787-791)
+ *
+ * Conventions: every function returns 0 on success or a negative svit_status; the message
+ * of the last failure on the calling thread is svit_last_error().  No C++ exception crosses
+ * the ABI.  The caller owns every buffer (device pointers, e.g. torch tensor.data_ptr());
+ * the library allocates nothing on the device.  Every launch is asynchronous on the given
+ * stream (a cudaStream_t, 0 = default stream) and never synchronises the host.
+ * All strides are in ELEMENTS of the pointed-to type.
+ */
+#ifndef SVIT_H_
+#define SVIT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVIT_ABI_VERSION 1
+
+typedef void* svit_stream_t; /* cudaStream_t */
+
+enum svit_status {
+  SVIT_OK = 0,
+  SVIT_ERR_ARG = -1,         /* bad argument (null pointer, size out of range) */
+  SVIT_ERR_ALIGN = -2,       /* pointer / stride alignment requirement violated */
+  SVIT_ERR_CUDA = -3,        /* a CUDA runtime / driver call failed */
+  SVIT_ERR_UNSUPPORTED = -4, /* valid request this build cannot serve */
+  SVIT_ERR_NO_DEVICE = -5    /* no sm_100 device available */
+};
+
+enum svit_dtype { SVIT_F32 = 0, SVIT_BF16 = 1, SVIT_F16 = 2 };
+
+/* Arithmetic of the dense contractions in the forward.  Accumulation is always fp32; the
+ * residual stream, LayerNorm statistics, softmax and the classifier head are always fp32. */
+enum svit_precision {
+  SVIT_PREC_F32 = 0,  /* fp32 operands, CUDA-core FMA GEMMs: the exact mode (small cases) */
+  SVIT_PREC_TF32 = 1, /* fp32 storage, tcgen05 kind::tf32 */
+  SVIT_PREC_BF16 = 2, /* bf16 operands, tcgen05 kind::f16 */
+  SVIT_PREC_F16 = 3   /* fp16 operands, tcgen05 kind::f16 (same rate as bf16, 3 more mantissa bits) */
+};
+
+typedef struct svit_vit_cfg {
+  int32_t hidden, layers, heads, ff, image, patch, channels, n_cls;
+  float ln_eps;
+} svit_vit_cfg;
+
+/* ---- library ------------------------------------------------------------------------ */
+const char* svit_version(void);
+const char* svit_last_error(void);
+/* Number of SMs and compute capability of the current device; SVIT_ERR_NO_DEVICE if none. */
+int svit_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- plan layout -------------------------------------------------------------------- */
+/* A model is one row [vec region (always fp32) | mat region (GEMM operand dtype)]; every
+ * segment starts on a 64-element boundary.  Mirrors shapley_vit_b200/layout.py. */
+enum svit_region { SVIT_REGION_VEC = 0, SVIT_REGION_MAT = 1 };
+enum svit_seg_kind {
+  SVIT_SEG_CLS = 0, SVIT_SEG_POS, SVIT_SEG_PATCH_B, SVIT_SEG_LN1_G, SVIT_SEG_LN1_B, SVIT_SEG_BQ,
+  SVIT_SEG_BK, SVIT_SEG_BV, SVIT_SEG_BO, SVIT_SEG_LN2_G, SVIT_SEG_LN2_B, SVIT_SEG_B1, SVIT_SEG_B2,
+  SVIT_SEG_LNF_G, SVIT_SEG_LNF_B, SVIT_SEG_HEAD_W, SVIT_SEG_HEAD_B,
+  SVIT_SEG_PATCH_W, SVIT_SEG_WQ, SVIT_SEG_WK, SVIT_SEG_WV, SVIT_SEG_WO, SVIT_SEG_W1, SVIT_SEG_W2,
+  SVIT_SEG_KINDS
+};
+typedef struct svit_segment {
+  int32_t kind, layer /* -1 if not per-layer */, region;
+  int32_t reserved;
+  int64_t offset /* elements from the start of the region */, size, rows, cols;
+} svit_segment;
+int svit_layout_sizes(const svit_vit_cfg* cfg, int64_t* vec_size, int64_t* mat_size, int32_t* n_segments);
+int svit_layout_segment(const svit_vit_cfg* cfg, int32_t index, svit_segment* out);
+
+/* ---- K1: coalition aggregation -------------------------------------------------------
+ * out[c, p] = cast( w0[p] + sum_{j : ratios[c,j] != 0, ascending j} ratios[c,j] * deltas[j, p] )
+ * with every product and every sum rounded to fp32 separately (no FMA contraction), i.e. the
+ * arithmetic of get_aggregated_model followed by model_agg_lazy.  The [N, P] stack is read
+ * from HBM ONCE for all C coalitions.
+ *   deltas  device [N, delta_stride] fp32     w0   device [P] fp32 (NULL = zeros)
+ *   ratios  device [C, N] fp32, 0 for non-members (FedAvg n_j / sum n over the coalition)
+ *   out     device [C, out_stride] of out_dtype (SVIT_F32 / SVIT_BF16 / SVIT_F16)
+ * Requirements: deltas, w0, out 16-byte aligned; delta_stride and out_stride multiples of 8
+ * and >= P rounded up to 8; 1 <= N <= 64; 1 <= C <= 256. */
+int svit_aggregate(const float* deltas, int64_t delta_stride, const float* w0, const float* ratios,
+                   void* out, int64_t out_stride, int out_dtype, int64_t P, int N, int C,
+                   svit_stream_t stream);
+
+/* ---- forward ------------------------------------------------------------------------ */
+typedef struct svit_plan svit_plan; /* opaque: geometry, layout table, TMA descriptors */
+int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_coalitions, int max_images,
+                     svit_plan** out);
+int svit_plan_destroy(svit_plan* plan);
+/* Bytes of caller-provided device workspace svit_forward_batched needs for (C, B) up to the
+ * plan's maxima; 256-byte aligned. */
+int64_t svit_plan_workspace_bytes(const svit_plan* plan);
+/* dtype (svit_dtype) of the mat region / activations for this plan's precision. */
+int svit_plan_operand_dtype(const svit_plan* plan);
+
+/* images [n, channels, image, image] fp32 (NCHW) -> patches [n * n_patches, channels*patch*patch]
+ * in the plan's operand dtype, column order (channel, row, col) = the flattened conv kernel. */
+int svit_patchify(const svit_plan* plan, const float* images, void* patches, int64_t n,
+                  svit_stream_t stream);
+
+/* logits[c * logits_stride + b * n_cls + k] for c < C, b < B: the ViT forward of image b under
+ * the weights of coalition c.
+ *   wvec  device [C, vec_stride] fp32          (vec region, from svit_aggregate)
+ *   wmat  device [C, mat_stride] operand dtype (mat region, from svit_aggregate)
+ *   patches device [B * n_patches, patch_dim] operand dtype (from svit_patchify), shared by all C */
+int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat,
+                         int64_t mat_stride, const void* patches, float* logits, int64_t logits_stride,
+                         int C, int B, void* workspace, size_t workspace_bytes, svit_stream_t stream);
+
+/* ---- K5: scoring ---------------------------------------------------------------------
+ * For each coalition c: correct[c] (+)= #{i : argmax_k logits[c,i,k] == labels[i]} (first maximal
+ * index on ties, like torch.argmax), loss_sum[c] (+)= sum_i CE(logits[c,i,:], labels[i]) with fp32
+ * log-sum-exp per sample and a deterministic fp64 reduction.  pred (optional) receives the argmax.
+ *   logits device [C, logits_stride] fp32, rows of n_cls     labels device [n] int64
+ *   accumulate != 0 adds to correct / loss_sum instead of overwriting. */
+int svit_score(const float* logits, int64_t logits_stride, const int64_t* labels, int C, int64_t n,
+               int n_cls, int64_t* correct, double* loss_sum, int32_t* pred, int64_t pred_stride,
+               int accumulate, svit_stream_t stream);
+
+/* ---- building blocks (exported for per-kernel parity tests and roofline timing) ------ */
+typedef struct svit_epilogue {
+  const float* bias;     int64_t bias_gs;     /* [N] per group, NULL = none */
+  const float* rowvec;   int64_t rowvec_gs;   /* [rows_out, N] per group, added by (out_row % rows_out); NULL = none */
+  const float* residual; int64_t residual_gs; /* fp32 [M_out, N] per group, added last; may alias out */
+  int32_t gelu;                               /* exact-erf GELU after bias */
+  int32_t rows_in, rows_out, row_shift;       /* rows_in > 0: out_row = (r / rows_in) * rows_out + row_shift + r % rows_in */
+} svit_epilogue;
+
+/* For g < G: out[g] = epilogue( A[g] (M x K, row-major) * B[g]^T (B[g] is N x K, row-major) ).
+ * A, B in the operand dtype of `precision`; out_dtype is SVIT_F32 or that operand dtype.
+ * Group strides may be 0 (operand shared by all groups).  M_out = M unless rows_in > 0. */
+int svit_gemm(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, void* out,
+              int64_t out_gs, int out_dtype, int G, int M, int N, int K, const svit_epilogue* epi,
+              svit_stream_t stream);
+
+/* y[g, r, :] = LayerNorm(x[g, r, :]) * gamma[g] + beta[g]; x fp32 [G, rows, h] (row stride x_ld),
+ * y in out_dtype, biased variance, eps as given (HF ViT: 1e-12). */
+int svit_layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, const float* beta,
+                   int64_t param_gs, void* y, int64_t y_gs, int64_t y_ld, int out_dtype, int G,
+                   int64_t rows, int h, float eps, svit_stream_t stream);
+
+/* qkv [n_seq, T, 3h] (q | k | v, heads contiguous inside each) in `dtype` ->
+ * ctx [n_seq, T, h] = softmax(q k^T / sqrt(d)) v per head, fp32 softmax. */
+int svit_attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, int head_dim,
+                   svit_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVIT_H_ */

@@ -1,0 +1,143 @@
+// Fused-softmax attention for short, non-causal sequences (ViT: T = 197 at 224 px, 5 at 32 px).
+//
+// Restates HF ViTSelfAttention (modeling_vit.py:171-196, 220-252) as evaluated by the
+// reference (federated_learning/utils.py:886): per (sequence, head)
+//     ctx = softmax(q k^T * d^-0.5) v,   no mask, no dropout in eval.
+// The whole K and V of one head live in shared memory (T*d*4*2 bytes = 101 KB for T=197, d=64),
+// a warp owns one query row at a time: scores (7 keys per lane) -> fp32 softmax in registers ->
+// P V with two output channels per lane.  Scores never touch HBM.
+//
+// This is the fp32 CUDA-core kernel used by every precision mode in round 1; operands may be
+// stored in fp32 / bf16 / fp16, all arithmetic is fp32.
+#include "elementwise.h"
+
+namespace svit {
+namespace {
+
+constexpr int kAttWarps = 8;
+
+// dynamic smem: Ks [T][D+1] | Vs [T][D] | per-warp q [D] and p [Tpad]
+template <typename T, int D>
+__global__ void __launch_bounds__(kAttWarps * 32) attention_kernel(const T* __restrict__ qkv, T* __restrict__ ctx,
+                                                                   int Tn, int heads) {
+  extern __shared__ float att_smem[];
+  const int h = heads * D;
+  const int64_t seq = blockIdx.x;
+  const int head = blockIdx.y;
+  const int Tpad = (Tn + 31) & ~31;
+  float* Ks = att_smem;
+  float* Vs = Ks + (size_t)Tn * (D + 1);
+  float* wq = Vs + (size_t)Tn * D;
+  float* wp = wq + kAttWarps * D;
+  const T* base = qkv + seq * (int64_t)Tn * 3 * h;
+  for (int i = threadIdx.x; i < Tn * D; i += blockDim.x) {
+    const int t = i / D, d = i % D;
+    Ks[t * (D + 1) + d] = Cvt<T>::to_f(base[(size_t)t * 3 * h + h + head * D + d]);
+    Vs[t * D + d] = Cvt<T>::to_f(base[(size_t)t * 3 * h + 2 * h + head * D + d]);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q = wq + warp * D;
+  float* p = wp + warp * Tpad;
+  const float scale = rsqrtf((float)D);
+  constexpr int KPL = 8;  // keys per lane: supports T <= 256
+  for (int t = warp; t < Tn; t += kAttWarps) {
+    for (int d = lane; d < D; d += 32) q[d] = Cvt<T>::to_f(base[(size_t)t * 3 * h + head * D + d]);
+    __syncwarp();
+    float s[KPL];
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) s[k] = 0.f;
+    for (int d = 0; d < D; ++d) {
+      const float qd = q[d];
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) {
+        const int j = lane + k * 32;
+        if (j < Tn) s[k] = fmaf(qd, Ks[j * (D + 1) + d], s[k]);
+      }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      s[k] *= scale;
+      if (lane + k * 32 < Tn) m = fmaxf(m, s[k]);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int j = lane + k * 32;
+      s[k] = j < Tn ? expf(s[k] - m) : 0.f;
+      sum += s[k];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+      const int j = lane + k * 32;
+      if (j < Tpad) p[j] = s[k] * inv;
+    }
+    __syncwarp();
+    // P V: lane owns channels lane, lane+32, ...
+    float o[D / 32];
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) o[c] = 0.f;
+    for (int j = 0; j < Tn; ++j) {
+      const float pj = p[j];
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) o[c] = fmaf(pj, Vs[j * D + lane + c * 32], o[c]);
+    }
+    T* out = ctx + (seq * (int64_t)Tn + t) * h + head * D;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) out[lane + c * 32] = Cvt<T>::from_f(o[c]);
+    __syncwarp();
+  }
+}
+
+template <typename T, int D>
+int launch_att(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
+  const int Tpad = (Tn + 31) & ~31;
+  const size_t smem = ((size_t)Tn * (D + 1) + (size_t)Tn * D + kAttWarps * D + kAttWarps * Tpad) * sizeof(float);
+  SVIT_CHECK_ARG(smem <= 227 * 1024, "attention: T=%d does not fit shared memory", Tn);
+  auto kern = attention_kernel<T, D>;
+  SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SVIT_CHECK_ARG(n_seq <= 0x7fffffff, "attention: too many sequences");
+  dim3 grid((unsigned)n_seq, heads);
+  kern<<<grid, kAttWarps * 32, smem, stream>>>((const T*)qkv, (T*)ctx, Tn, heads);
+  SVIT_LAUNCH_CHECK("attention_kernel");
+  return SVIT_OK;
+}
+
+template <typename T>
+int dispatch_d(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, int head_dim, cudaStream_t stream) {
+  switch (head_dim) {
+    case 32: return launch_att<T, 32>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 64: return launch_att<T, 64>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 96: return launch_att<T, 96>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 128: return launch_att<T, 128>(qkv, ctx, n_seq, Tn, heads, stream);
+    default: SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "attention: head_dim %d not supported (32/64/96/128)", head_dim);
+  }
+}
+
+}  // namespace
+
+int attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, int heads, int head_dim,
+              cudaStream_t stream) {
+  if (n_seq == 0) return SVIT_OK;
+  SVIT_CHECK_ARG(Tn >= 1 && Tn <= 256, "attention: T=%d out of range (1..256)", Tn);
+  switch (dtype) {
+    case SVIT_F32: return dispatch_d<float>(qkv, ctx, n_seq, Tn, heads, head_dim, stream);
+    case SVIT_BF16: return dispatch_d<__nv_bfloat16>(qkv, ctx, n_seq, Tn, heads, head_dim, stream);
+    case SVIT_F16: return dispatch_d<__half>(qkv, ctx, n_seq, Tn, heads, head_dim, stream);
+    default: SVIT_FAIL(SVIT_ERR_ARG, "attention: bad dtype %d", dtype);
+  }
+}
+
+}  // namespace svit
+
+extern "C" int svit_attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, int head_dim,
+                              svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(qkv && ctx, "svit_attention: null pointer");
+  SVIT_CHECK_ARG(n_seq >= 0 && heads >= 1, "svit_attention: bad sizes");
+  return attention(qkv, ctx, dtype, n_seq, T, heads, head_dim, static_cast<cudaStream_t>(stream));
+}

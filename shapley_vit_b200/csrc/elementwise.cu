@@ -1,0 +1,229 @@
+// Bandwidth-bound pieces of the batched ViT forward: patch extraction, LayerNorm,
+// the [CLS] row of the embedding, and the classifier head (final LayerNorm on the CLS token +
+// Linear).  They restate, per coalition group g, what HF's modeling_vit.py does in
+// embeddings :100-128, layernorm_before/after :325-326, final layernorm :416 and the
+// classifier :641-642 for the model the reference evaluates (federated_learning/utils.py:886).
+#include "elementwise.h"
+
+namespace svit {
+namespace {
+
+// ---- patchify: NCHW fp32 images -> [n * np, C*ps*ps] rows in the operand dtype ------------
+template <typename T>
+__global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int64_t n, int C, int H, int ps) {
+  const int gw = H / ps;                       // patches per side
+  const int pd = C * ps * ps;                  // row length
+  const int q_per_row = pd / 4;                // float4 groups per output row
+  const int64_t total = n * gw * gw * (int64_t)q_per_row;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % q_per_row);
+    const int64_t row = i / q_per_row;
+    const int col = q * 4;
+    const int c = col / (ps * ps), ky = (col / ps) % ps, kx = col % ps;
+    const int64_t im = row / (gw * gw);
+    const int p = (int)(row % (gw * gw)), py = p / gw, px = p % gw;
+    const float4 v = *reinterpret_cast<const float4*>(
+        img + ((im * C + c) * H + (py * ps + ky)) * (int64_t)H + px * ps + kx);
+    store4<T>(out + row * pd + col, v.x, v.y, v.z, v.w);
+  }
+}
+
+// ---- LayerNorm: one warp per row, fp32 statistics, two-pass variance ----------------------
+constexpr int kLnMaxVec = 8;  // h <= 1024
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t x_gs, int64_t x_ld,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int64_t param_gs,
+                                                        T* __restrict__ y, int64_t y_gs, int64_t y_ld, int64_t rows,
+                                                        int64_t total_rows, int h, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= total_rows) return;
+  const int64_t g = r / rows, rr = r % rows;
+  const float* xr = x + g * x_gs + rr * x_ld;
+  const int h4 = h >> 2;
+  float4 v[kLnMaxVec];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < h4) {
+      v[i] = reinterpret_cast<const float4*>(xr)[idx];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)h;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (lane + i * 32 < h4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)h + eps);
+  const float* gm = gamma + g * param_gs;
+  const float* bt = beta + g * param_gs;
+  T* yr = y + g * y_gs + rr * y_ld;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < h4) {
+      const float4 gg = reinterpret_cast<const float4*>(gm)[idx], bb = reinterpret_cast<const float4*>(bt)[idx];
+      store4<T>(yr + idx * 4, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+                (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+    }
+  }
+}
+
+// ---- [CLS] rows: X[g, b*T, :] = cls[g] + pos[g][0, :] -------------------------------------
+__global__ void embed_cls_kernel(float* __restrict__ X, int64_t x_gs, const float* __restrict__ wvec,
+                                 int64_t vec_stride, int64_t off_cls, int64_t off_pos, int B, int T, int h) {
+  const int g = blockIdx.y;
+  const float* cls = wvec + (size_t)g * vec_stride + off_cls;
+  const float* pos = wvec + (size_t)g * vec_stride + off_pos;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)B * h;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / h), k = (int)(i % h);
+    X[(size_t)g * x_gs + (size_t)b * T * h + k] = cls[k] + pos[k];
+  }
+}
+
+// ---- head: final LayerNorm on the CLS token + classifier, one warp per (g, image) ----------
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ X, int64_t x_gs,
+                                                   const float* __restrict__ wvec, int64_t vec_stride, int64_t off_g,
+                                                   int64_t off_b, int64_t off_w, int64_t off_hb,
+                                                   float* __restrict__ logits, int64_t logits_stride, int G, int B, int T,
+                                                   int h, int n_cls, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= (int64_t)G * B) return;
+  const int g = (int)(r / B), b = (int)(r % B);
+  const float* xr = X + (size_t)g * x_gs + (size_t)b * T * h;
+  const float* wv = wvec + (size_t)g * vec_stride;
+  const int h4 = h >> 2;
+  float4 v[kLnMaxVec];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < h4) {
+      v[i] = reinterpret_cast<const float4*>(xr)[idx];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)h;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    if (lane + i * 32 < h4) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + bb * bb) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)h + eps);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < h4) {
+      const float4 gg = reinterpret_cast<const float4*>(wv + off_g)[idx];
+      const float4 be = reinterpret_cast<const float4*>(wv + off_b)[idx];
+      v[i].x = (v[i].x - mean) * rstd * gg.x + be.x;
+      v[i].y = (v[i].y - mean) * rstd * gg.y + be.y;
+      v[i].z = (v[i].z - mean) * rstd * gg.z + be.z;
+      v[i].w = (v[i].w - mean) * rstd * gg.w + be.w;
+    }
+  }
+  for (int k = 0; k < n_cls; ++k) {
+    const float* wk = wv + off_w + (size_t)k * h;
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < h4) {
+        const float4 ww = reinterpret_cast<const float4*>(wk)[idx];
+        dot += (v[i].x * ww.x + v[i].y * ww.y) + (v[i].z * ww.z + v[i].w * ww.w);
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) logits[(size_t)g * logits_stride + (size_t)b * n_cls + k] = dot + wv[off_hb + k];
+  }
+}
+
+}  // namespace
+
+int patchify(int dtype, const float* images, void* patches, int64_t n, int C, int H, int ps, cudaStream_t stream) {
+  if (n == 0) return SVIT_OK;
+  SVIT_CHECK_ARG(ps % 4 == 0 && H % ps == 0, "patchify: patch must be a multiple of 4 and divide the image");
+  const int64_t total = n * (H / ps) * (H / ps) * (int64_t)(C * ps * ps / 4);
+  const int block = 256;
+  const int grid = (int)std::min<int64_t>((total + block - 1) / block, (int64_t)sm_count() * 16);
+  switch (dtype) {
+    case SVIT_F32: patchify_kernel<float><<<grid, block, 0, stream>>>(images, (float*)patches, n, C, H, ps); break;
+    case SVIT_BF16:
+      patchify_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(images, (__nv_bfloat16*)patches, n, C, H, ps);
+      break;
+    case SVIT_F16: patchify_kernel<__half><<<grid, block, 0, stream>>>(images, (__half*)patches, n, C, H, ps); break;
+    default: SVIT_FAIL(SVIT_ERR_ARG, "patchify: bad dtype %d", dtype);
+  }
+  SVIT_LAUNCH_CHECK("patchify_kernel");
+  return SVIT_OK;
+}
+
+int layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, const float* beta, int64_t param_gs,
+              void* y, int64_t y_gs, int64_t y_ld, int out_dtype, int G, int64_t rows, int h, float eps,
+              cudaStream_t stream) {
+  SVIT_CHECK_ARG(h % 4 == 0 && h <= kLnMaxVec * 128, "layernorm: h=%d must be a multiple of 4 and <= 1024", h);
+  SVIT_CHECK_ARG(x_ld % 4 == 0 && y_ld % 4 == 0 && x_gs % 4 == 0 && param_gs % 4 == 0, "layernorm: strides must be multiples of 4");
+  const int64_t total = (int64_t)G * rows;
+  if (total == 0) return SVIT_OK;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
+#define SVIT_LN(T)                                                                                                  \
+  layernorm_kernel<T><<<grid, wpb * 32, 0, stream>>>(x, x_gs, x_ld, gamma, beta, param_gs, (T*)y, y_gs, y_ld, rows, \
+                                                     total, h, eps)
+  switch (out_dtype) {
+    case SVIT_F32: SVIT_LN(float); break;
+    case SVIT_BF16: SVIT_LN(__nv_bfloat16); break;
+    case SVIT_F16: SVIT_LN(__half); break;
+    default: SVIT_FAIL(SVIT_ERR_ARG, "layernorm: bad dtype %d", out_dtype);
+  }
+#undef SVIT_LN
+  SVIT_LAUNCH_CHECK("layernorm_kernel");
+  return SVIT_OK;
+}
+
+int embed_cls(float* X, int64_t x_gs, const float* wvec, int64_t vec_stride, int64_t off_cls, int64_t off_pos, int G,
+              int B, int T, int h, cudaStream_t stream) {
+  dim3 grid((unsigned)std::min<int64_t>(((int64_t)B * h + 255) / 256, 1024), G);
+  embed_cls_kernel<<<grid, 256, 0, stream>>>(X, x_gs, wvec, vec_stride, off_cls, off_pos, B, T, h);
+  SVIT_LAUNCH_CHECK("embed_cls_kernel");
+  return SVIT_OK;
+}
+
+int head(const float* X, int64_t x_gs, const float* wvec, int64_t vec_stride, int64_t off_g, int64_t off_b,
+         int64_t off_w, int64_t off_hb, float* logits, int64_t logits_stride, int G, int B, int T, int h, int n_cls,
+         float eps, cudaStream_t stream) {
+  SVIT_CHECK_ARG(h % 4 == 0 && h <= kLnMaxVec * 128, "head: h=%d unsupported", h);
+  const int64_t total = (int64_t)G * B;
+  const int wpb = 8;
+  head_kernel<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      X, x_gs, wvec, vec_stride, off_g, off_b, off_w, off_hb, logits, logits_stride, G, B, T, h, n_cls, eps);
+  SVIT_LAUNCH_CHECK("head_kernel");
+  return SVIT_OK;
+}
+
+}  // namespace svit
+
+extern "C" int svit_layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, const float* beta,
+                              int64_t param_gs, void* y, int64_t y_gs, int64_t y_ld, int out_dtype, int G, int64_t rows,
+                              int h, float eps, svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(x && gamma && beta && y, "svit_layernorm: null pointer");
+  SVIT_CHECK_ARG(G >= 1 && rows >= 0, "svit_layernorm: bad sizes");
+  if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(y))
+    SVIT_FAIL(SVIT_ERR_ALIGN, "svit_layernorm: pointers must be 16-byte aligned");
+  return layernorm(x, x_gs, x_ld, gamma, beta, param_gs, y, y_gs, y_ld, out_dtype, G, rows, h, eps,
+                   static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,234 @@
+// Batched multi-coalition ViT forward: svit_plan_*, svit_patchify, svit_forward_batched,
+// svit_gemm.
+//
+// Replaces `net(img).logits` inside the reference's evaluation loop
+// (federated_learning/utils.py:880-886) for C coalition models at once.  Every dense layer is a
+// GROUPED GEMM over the coalition axis (group g reads the g-th row of the aggregated weight
+// matrix region written by svit_aggregate); activations of all groups live side by side in one
+// caller-provided workspace:
+//
+//   X    fp32     [C, B*T, h]   residual stream (always fp32)
+//   Xn   operand  [C, B*T, h]   LayerNorm output (GEMM A operand)
+//   QKV  operand  [C, B*T, 3h]
+//   CTX  operand  [C, B*T, h]   attention output
+//   H    operand  [C, B*T, ff]  GELU(MLP up)
+//
+// Per layer: LN -> QKV GEMM(+bias) -> fused-softmax attention -> proj GEMM(+bias +residual, in
+// place on X) -> LN -> MLP-up GEMM(+bias +GELU) -> MLP-down GEMM(+bias +residual).  The patch
+// embedding is one GEMM whose A operand (the patchified validation images) is shared by all
+// coalitions; its epilogue adds the conv bias and the position embedding and leaves the [CLS]
+// row gap.  The head (final LN on CLS + classifier) is one fp32 warp per (coalition, image).
+#include <cstdlib>
+#include <new>
+
+#include "elementwise.h"
+#include "epilogue.cuh"
+#include "layout.h"
+
+struct svit_plan {
+  svit::Layout lay;
+  int precision = 0, operand_dtype = 0;
+  int max_c = 0, max_b = 0;
+  int T = 0, np = 0, pd = 0;
+  bool force_simt = false;
+  // workspace byte offsets for (max_c, max_b)
+  size_t off_x = 0, off_xn = 0, off_qkv = 0, off_ctx = 0, off_h = 0, ws_bytes = 0;
+};
+
+namespace svit {
+namespace {
+
+int operand_dtype_of(int precision) {
+  switch (precision) {
+    case SVIT_PREC_F32:
+    case SVIT_PREC_TF32: return SVIT_F32;
+    case SVIT_PREC_BF16: return SVIT_BF16;
+    case SVIT_PREC_F16: return SVIT_F16;
+    default: return -1;
+  }
+}
+
+int gemm_dispatch(const svit_plan* p, const void* A, int64_t a_gs, const void* B, int64_t b_gs, int G, int M, int N,
+                  int K, const EpiArgs& epi, cudaStream_t stream) {
+  if (p->precision == SVIT_PREC_F32 || p->force_simt)
+    return gemm_simt(p->operand_dtype, A, a_gs, B, b_gs, G, M, N, K, epi, stream);
+  return gemm_tc(p->precision, A, a_gs, B, b_gs, G, M, N, K, epi, stream);
+}
+
+}  // namespace
+}  // namespace svit
+
+extern "C" int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_coalitions, int max_images,
+                                svit_plan** out) {
+  using namespace svit;
+  SVIT_CHECK_ARG(out != nullptr, "svit_plan_create: out is null");
+  *out = nullptr;
+  SVIT_CHECK_ARG(max_coalitions >= 1 && max_images >= 1, "svit_plan_create: max_coalitions/max_images must be >= 1");
+  const int odt = operand_dtype_of(precision);
+  SVIT_CHECK_ARG(odt >= 0, "svit_plan_create: unknown precision %d", precision);
+  svit_plan* p = new (std::nothrow) svit_plan();
+  SVIT_CHECK_ARG(p != nullptr, "svit_plan_create: out of host memory");
+  int rc = build_layout(cfg, &p->lay);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  if (cfg->hidden > 1024 || (cfg->hidden / cfg->heads) % 32 != 0) {
+    delete p;
+    SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "svit_plan_create: hidden <= 1024 and head_dim %% 32 == 0 required");
+  }
+  p->precision = precision;
+  p->operand_dtype = odt;
+  p->max_c = max_coalitions;
+  p->max_b = max_images;
+  p->np = (cfg->image / cfg->patch) * (cfg->image / cfg->patch);
+  p->T = p->np + 1;
+  p->pd = cfg->channels * cfg->patch * cfg->patch;
+  const char* env = getenv("SVIT_FORCE_SIMT_GEMM");  // debugging aid: CUDA-core GEMMs on 16-bit operands
+  p->force_simt = env && env[0] == '1';
+  const size_t rows = (size_t)max_coalitions * max_images * p->T;
+  const size_t es = (size_t)dtype_size(odt);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  p->off_x = take(rows * cfg->hidden * 4);
+  p->off_xn = take(rows * cfg->hidden * es);
+  p->off_qkv = take(rows * 3 * cfg->hidden * es);
+  p->off_ctx = take(rows * cfg->hidden * es);
+  p->off_h = take(rows * cfg->ff * es);
+  p->ws_bytes = off;
+  *out = p;
+  return SVIT_OK;
+}
+
+extern "C" int svit_plan_destroy(svit_plan* plan) {
+  delete plan;
+  return SVIT_OK;
+}
+
+extern "C" int64_t svit_plan_workspace_bytes(const svit_plan* plan) { return plan ? (int64_t)plan->ws_bytes : -1; }
+extern "C" int svit_plan_operand_dtype(const svit_plan* plan) { return plan ? plan->operand_dtype : -1; }
+
+extern "C" int svit_patchify(const svit_plan* plan, const float* images, void* patches, int64_t n,
+                             svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(plan && images && patches && n >= 0, "svit_patchify: bad arguments");
+  if (!aligned16(images) || !aligned16(patches)) SVIT_FAIL(SVIT_ERR_ALIGN, "svit_patchify: pointers must be 16-byte aligned");
+  const svit_vit_cfg& c = plan->lay.cfg;
+  return patchify(plan->operand_dtype, images, patches, n, c.channels, c.image, c.patch, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat,
+                                    int64_t mat_stride, const void* patches, float* logits, int64_t logits_stride,
+                                    int C, int B, void* workspace, size_t workspace_bytes, svit_stream_t stream_) {
+  using namespace svit;
+  SVIT_CHECK_ARG(plan && wvec && wmat && patches && logits && workspace, "svit_forward_batched: null pointer");
+  SVIT_CHECK_ARG(C >= 1 && C <= plan->max_c && B >= 1 && B <= plan->max_b,
+                 "svit_forward_batched: (C=%d, B=%d) exceeds the plan's (%d, %d)", C, B, plan->max_c, plan->max_b);
+  SVIT_CHECK_ARG(workspace_bytes >= plan->ws_bytes, "svit_forward_batched: workspace too small (%zu < %zu)",
+                 workspace_bytes, plan->ws_bytes);
+  const svit_vit_cfg& cfg = plan->lay.cfg;
+  const Layout& L = plan->lay;
+  SVIT_CHECK_ARG(vec_stride >= L.vec_size && mat_stride >= L.mat_size && vec_stride % 64 == 0 && mat_stride % 64 == 0,
+                 "svit_forward_batched: weight strides must be multiples of 64 and cover the layout");
+  SVIT_CHECK_ARG(logits_stride >= (int64_t)B * cfg.n_cls, "svit_forward_batched: logits_stride too small");
+  if (!aligned16(wvec) || !aligned16(wmat) || !aligned16(patches) || ((uintptr_t)workspace & 255))
+    SVIT_FAIL(SVIT_ERR_ALIGN, "svit_forward_batched: weights/patches must be 16-byte and workspace 256-byte aligned");
+
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int h = cfg.hidden, ff = cfg.ff, T = plan->T, np = plan->np, pd = plan->pd;
+  const int M = B * T;
+  const int odt = plan->operand_dtype;
+  const size_t es = (size_t)dtype_size(odt);
+  char* ws = static_cast<char*>(workspace);
+  float* X = reinterpret_cast<float*>(ws + plan->off_x);
+  void* Xn = ws + plan->off_xn;
+  void* QKV = ws + plan->off_qkv;
+  void* CTX = ws + plan->off_ctx;
+  void* H = ws + plan->off_h;
+  const char* wm = static_cast<const char*>(wmat);
+  auto mat = [&](int kind, int layer) -> const void* { return wm + (size_t)L.find(kind, layer) * es; };
+  auto vec = [&](int kind, int layer) -> const float* { return wvec + L.find(kind, layer); };
+  const int64_t xgs = (int64_t)M * h;
+  int rc;
+
+  // ---- embeddings ----
+  if ((rc = embed_cls(X, xgs, wvec, vec_stride, L.find(SVIT_SEG_CLS), L.find(SVIT_SEG_POS), C, B, T, h, stream))) return rc;
+  {
+    svit_epilogue e{};
+    e.bias = vec(SVIT_SEG_PATCH_B, -1);
+    e.bias_gs = vec_stride;
+    e.rowvec = vec(SVIT_SEG_POS, -1);
+    e.rowvec_gs = vec_stride;
+    e.rows_in = np;
+    e.rows_out = T;
+    e.row_shift = 1;
+    EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, B * np, h);
+    if ((rc = gemm_dispatch(plan, patches, 0, mat(SVIT_SEG_PATCH_W, -1), mat_stride, C, B * np, h, pd, ea, stream))) return rc;
+  }
+  // ---- encoder ----
+  for (int l = 0; l < cfg.layers; ++l) {
+    if ((rc = layernorm(X, xgs, h, vec(SVIT_SEG_LN1_G, l), vec(SVIT_SEG_LN1_B, l), vec_stride, Xn, xgs, h, odt, C, M, h,
+                        cfg.ln_eps, stream)))
+      return rc;
+    {
+      svit_epilogue e{};
+      e.bias = vec(SVIT_SEG_BQ, l);  // bq | bk | bv are contiguous
+      e.bias_gs = vec_stride;
+      EpiArgs ea = make_epi(&e, QKV, (int64_t)M * 3 * h, odt, M, 3 * h);
+      if ((rc = gemm_dispatch(plan, Xn, xgs, mat(SVIT_SEG_WQ, l), mat_stride, C, M, 3 * h, h, ea, stream))) return rc;
+    }
+    if ((rc = attention(QKV, CTX, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream))) return rc;
+    {
+      svit_epilogue e{};
+      e.bias = vec(SVIT_SEG_BO, l);
+      e.bias_gs = vec_stride;
+      e.residual = X;
+      e.residual_gs = xgs;
+      EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, M, h);
+      if ((rc = gemm_dispatch(plan, CTX, xgs, mat(SVIT_SEG_WO, l), mat_stride, C, M, h, h, ea, stream))) return rc;
+    }
+    if ((rc = layernorm(X, xgs, h, vec(SVIT_SEG_LN2_G, l), vec(SVIT_SEG_LN2_B, l), vec_stride, Xn, xgs, h, odt, C, M, h,
+                        cfg.ln_eps, stream)))
+      return rc;
+    {
+      svit_epilogue e{};
+      e.bias = vec(SVIT_SEG_B1, l);
+      e.bias_gs = vec_stride;
+      e.gelu = 1;
+      EpiArgs ea = make_epi(&e, H, (int64_t)M * ff, odt, M, ff);
+      if ((rc = gemm_dispatch(plan, Xn, xgs, mat(SVIT_SEG_W1, l), mat_stride, C, M, ff, h, ea, stream))) return rc;
+    }
+    {
+      svit_epilogue e{};
+      e.bias = vec(SVIT_SEG_B2, l);
+      e.bias_gs = vec_stride;
+      e.residual = X;
+      e.residual_gs = xgs;
+      EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, M, h);
+      if ((rc = gemm_dispatch(plan, H, (int64_t)M * ff, mat(SVIT_SEG_W2, l), mat_stride, C, M, h, ff, ea, stream))) return rc;
+    }
+  }
+  // ---- head ----
+  return head(X, xgs, wvec, vec_stride, L.find(SVIT_SEG_LNF_G), L.find(SVIT_SEG_LNF_B), L.find(SVIT_SEG_HEAD_W),
+              L.find(SVIT_SEG_HEAD_B), logits, logits_stride, C, B, T, h, cfg.n_cls, cfg.ln_eps, stream);
+}
+
+extern "C" int svit_gemm(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, void* out,
+                         int64_t out_gs, int out_dtype, int G, int M, int N, int K, const svit_epilogue* epi,
+                         svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(A && B && out, "svit_gemm: null pointer");
+  SVIT_CHECK_ARG(G >= 1 && M >= 1 && N >= 1 && K >= 1, "svit_gemm: bad sizes");
+  const int odt = operand_dtype_of(precision);
+  SVIT_CHECK_ARG(odt >= 0, "svit_gemm: unknown precision %d", precision);
+  SVIT_CHECK_ARG(out_dtype == SVIT_F32 || out_dtype == odt, "svit_gemm: out_dtype must be f32 or the operand dtype");
+  EpiArgs ea = make_epi(epi, out, out_gs, out_dtype, M, N);
+  const char* env = getenv("SVIT_FORCE_SIMT_GEMM");
+  if (precision == SVIT_PREC_F32 || (env && env[0] == '1'))
+    return gemm_simt(odt, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
+  return gemm_tc(precision, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,215 @@
+"""CoalitionEngine: device-resident state of one utility game and the batched evaluation of
+coalitions through libsvit.
+
+What the reference does per coalition (``Game.eval_utility``, reference
+fed_client_contribution/game.py:88-107): build FedAvg ratios, aggregate the member deltas,
+add W0, ``load_state_dict``, then run ``evaluation`` over the whole validation loader with
+an H2D copy per batch and two host syncs per batch.  Here, per BATCH of coalitions:
+
+    ratios [C, N] (host, fp64 -> fp32)  --H2D-->
+    svit_aggregate (vec region, fp32)  +  svit_aggregate (mat region, operand dtype)
+    for each chunk of validation images:  svit_forward_batched -> logits [C, n_val, n_cls]
+    svit_score -> correct [C] int64, loss_sum [C] fp64   --D2H-->
+
+The stacked client deltas, W0, the patchified validation set and the labels are uploaded
+once and stay in HBM.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+from .layout import PlanLayout, VitConfig, pack_state_dict, plan_layout
+
+
+class ValidationSet:
+    """The held-out validation set, resident in HBM: images are uploaded once and turned into
+    the patch matrix [n * n_patches, patch_dim] (the A operand of the patch-embedding GEMM,
+    shared by every coalition); labels as int64.  The reference instead re-uploads every batch
+    for every coalition (federated_learning/utils.py:880-882)."""
+
+    def __init__(self, cfg: VitConfig, images: torch.Tensor, labels: torch.Tensor, precision: int,
+                 device: str | torch.device = "cuda:0"):
+        self.cfg, self.precision, self.device = cfg, precision, torch.device(device)
+        self.n = int(images.shape[0])
+        if tuple(images.shape[1:]) != (cfg.channels, cfg.image, cfg.image):
+            raise ValueError(f"images must be [n, {cfg.channels}, {cfg.image}, {cfg.image}], got {tuple(images.shape)}")
+        with torch.cuda.device(self.device):
+            helper = ops.Plan(cfg, precision, 1, 1, self.device)
+            self.operand_dtype = helper.operand_dtype
+            self.patches = torch.empty((self.n * cfg.n_patches, cfg.patch_dim), dtype=self.operand_dtype,
+                                       device=self.device)
+            self.upload(images, labels, helper)
+            helper.close()
+
+    def upload(self, images: torch.Tensor, labels: torch.Tensor, plan=None) -> int:
+        """(Re-)upload host images/labels; returns the bytes copied host -> device."""
+        cfg = self.cfg
+        own = plan is None
+        with torch.cuda.device(self.device):
+            if own:
+                plan = ops.Plan(cfg, self.precision, 1, 1, self.device)
+            step = 1024
+            for s in range(0, self.n, step):
+                img = images[s:s + step].to(self.device, dtype=torch.float32, non_blocking=True)
+                plan.patchify(img, out=self.patches[s * cfg.n_patches:(s + img.shape[0]) * cfg.n_patches])
+            self.labels = labels.to(self.device, dtype=torch.int64, non_blocking=True).contiguous()
+            if own:
+                torch.cuda.current_stream().synchronize()
+                plan.close()
+        return images.numel() * 4 + labels.numel() * 8
+
+    @staticmethod
+    def from_loader(cfg: VitConfig, loader, precision: int, device="cuda:0") -> "ValidationSet":
+        """Drain a DataLoader of the reference's dict samples {'image','label',...}
+        (federated_learning/utils.py:880) or of (x, y) tuples."""
+        imgs, labs = [], []
+        for sample in loader:
+            if isinstance(sample, dict):
+                x, y = sample["image"], sample["label"]
+            else:
+                x, y = sample[0], sample[1]
+            imgs.append(torch.as_tensor(x, dtype=torch.float32))
+            labs.append(torch.as_tensor(y).long().reshape(-1))
+        return ValidationSet(cfg, torch.cat(imgs), torch.cat(labs), precision, device)
+
+
+class CoalitionEngine:
+    def __init__(self, cfg: VitConfig, w0: Optional[Dict[str, torch.Tensor]],
+                 deltas: Sequence[Dict[str, torch.Tensor]], images, labels: Optional[torch.Tensor] = None,
+                 precision: str = "f16", coalition_batch: int = 8, image_chunk: int = 128,
+                 device: str | torch.device = "cuda:0", keep_logits: bool = False):
+        """``images`` is either a host tensor [n, C, H, W] (with ``labels``) or a ValidationSet."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("CoalitionEngine needs a CUDA device (sm_100a); there is no CPU path")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.lay: PlanLayout = plan_layout(cfg)
+        self.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        self.n_clients = len(deltas)
+        if not 1 <= self.n_clients <= 64:
+            raise ValueError("1..64 clients supported")
+        self.n_val = images.n if isinstance(images, ValidationSet) else int(images.shape[0])
+        self.coalition_batch = max(1, int(coalition_batch))
+        self.image_chunk = max(1, min(int(image_chunk), self.n_val))
+        self.keep_logits = keep_logits
+        self.last_logits: Optional[torch.Tensor] = None
+        self.kernel_launches = 0
+        with torch.cuda.device(self.device):
+            self.plan = ops.Plan(cfg, self.precision, self.coalition_batch, self.image_chunk, self.device)
+            total = self.lay.total
+            # stacked deltas [N, total] and W0 [total], plan layout, fp32, resident
+            host = torch.empty((self.n_clients, total), dtype=torch.float32, pin_memory=True)
+            for j, d in enumerate(deltas):
+                pack_state_dict(self.lay, d, out=host[j])
+            self.deltas = host.to(self.device, non_blocking=True)
+            if w0 is not None:
+                self.w0 = pack_state_dict(self.lay, w0).to(self.device)
+            else:
+                self.w0 = None
+            self.val = images if isinstance(images, ValidationSet) else ValidationSet(
+                cfg, images, labels, self.precision, self.device)
+            if self.val.precision != self.precision or self.val.device != self.device:
+                raise ValueError("ValidationSet was built for another precision/device")
+            cb = self.coalition_batch
+            self.wvec = torch.empty((cb, self.lay.vec_size), dtype=torch.float32, device=self.device)
+            self.wmat = torch.empty((cb, self.lay.mat_size), dtype=self.plan.operand_dtype, device=self.device)
+            self.logits = torch.empty((cb, self.n_val, cfg.n_cls), dtype=torch.float32, device=self.device)
+            # ring of pinned staging rows for the per-batch ratio upload (reused only after the
+            # copy that read them has completed)
+            self._ring = [(torch.zeros((cb, self.n_clients), dtype=torch.float32, pin_memory=True),
+                           torch.zeros((cb, self.n_clients), dtype=torch.float32, device=self.device),
+                           torch.cuda.Event()) for _ in range(4)]
+            self._ring_pos = 0
+            torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ #
+    @property
+    def patches(self) -> torch.Tensor:
+        return self.val.patches
+
+    @property
+    def labels(self) -> torch.Tensor:
+        return self.val.labels
+
+    def upload_bytes_per_batch(self) -> int:
+        return self.coalition_batch * self.n_clients * 4
+
+    # ------------------------------------------------------------------ #
+    def _run_batch(self, ratio_rows: Sequence[Sequence[float]]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One batch of <= coalition_batch coalitions given their dense ratio rows."""
+        Cn = len(ratio_rows)
+        lay, cfg = self.lay, self.cfg
+        rh, rd, ev = self._ring[self._ring_pos]
+        self._ring_pos = (self._ring_pos + 1) % len(self._ring)
+        ev.synchronize()
+        rh.zero_()
+        rh[:Cn] = torch.as_tensor(ratio_rows, dtype=torch.float64).to(torch.float32)
+        rd.copy_(rh, non_blocking=True)
+        ev.record()
+        ratios = rd[:Cn]
+        V, Mz = lay.vec_size, lay.mat_size
+        w0v = self.w0[:V] if self.w0 is not None else None
+        w0m = self.w0[V:] if self.w0 is not None else None
+        ops.aggregate(self.deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
+        ops.aggregate(self.deltas[:, V:], w0m, ratios, out=self.wmat[:Cn], P=Mz)
+        logits = self.logits[:Cn]
+        npch = cfg.n_patches
+        for s in range(0, self.n_val, self.image_chunk):
+            b = min(self.image_chunk, self.n_val - s)
+            self.plan.forward(self.wvec[:Cn], self.wmat[:Cn], self.patches[s * npch:(s + b) * npch], b, logits,
+                              image_offset=s)
+        self.kernel_launches += 2 + ((self.n_val + self.image_chunk - 1) // self.image_chunk) * (3 + 7 * cfg.layers) + 1
+        correct, loss = ops.score(logits, self.labels)
+        if self.keep_logits:
+            self.last_logits = logits.clone()
+        return correct, loss
+
+    def ratio_row(self, members: Sequence[int], ratios: Sequence[float]) -> List[float]:
+        row = [0.0] * self.n_clients
+        for j, r in zip(members, ratios):
+            row[int(j)] = float(r)
+        return row
+
+    def evaluate(self, ratio_rows: Sequence[Sequence[float]]) -> Tuple[List[int], List[float]]:
+        """Evaluate coalitions given as dense FedAvg ratio rows [n_clients] (0 = non-member).
+        Returns per coalition (#correct, sum of cross-entropy) over the validation set."""
+        correct: List[int] = []
+        loss: List[float] = []
+        with torch.cuda.device(self.device):
+            pending = []
+            for s in range(0, len(ratio_rows), self.coalition_batch):
+                c, l = self._run_batch(ratio_rows[s:s + self.coalition_batch])
+                pending.append((c, l))
+            for c, l in pending:       # single host sync at the end
+                correct += c.cpu().tolist()
+                loss += l.cpu().tolist()
+        return correct, loss
+
+    def evaluate_state_dict(self, sd: Dict[str, torch.Tensor]) -> Tuple[int, float]:
+        """Score one explicit model (the reference's plain ``evaluation(args, net, loader)``)."""
+        with torch.cuda.device(self.device):
+            row = pack_state_dict(self.lay, sd).to(self.device).unsqueeze(0)
+            one = torch.ones((1, 1), dtype=torch.float32, device=self.device)
+            V = self.lay.vec_size
+            ops.aggregate(row[:, :V], None, one, out=self.wvec[:1], P=V)
+            ops.aggregate(row[:, V:], None, one, out=self.wmat[:1], P=self.lay.mat_size)
+            logits = self.logits[:1]
+            npch = self.cfg.n_patches
+            for s in range(0, self.n_val, self.image_chunk):
+                b = min(self.image_chunk, self.n_val - s)
+                self.plan.forward(self.wvec[:1], self.wmat[:1], self.patches[s * npch:(s + b) * npch], b, logits,
+                                  image_offset=s)
+            correct, loss = ops.score(logits, self.labels)
+            if self.keep_logits:
+                self.last_logits = logits.clone()
+            return int(correct.item()), float(loss.item())
+
+    def aggregated_rows(self, ratio_rows: Sequence[Sequence[float]], dtype=torch.float32) -> torch.Tensor:
+        """Aggregated models (plan layout, [C, total]) for parity checks of K1."""
+        with torch.cuda.device(self.device):
+            r = torch.as_tensor(ratio_rows, dtype=torch.float64).to(torch.float32).to(self.device)
+            return ops.aggregate(self.deltas, self.w0, r, out_dtype=dtype)

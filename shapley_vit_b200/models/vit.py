@@ -1,0 +1,109 @@
+"""ViT definition whose ``state_dict()`` is key-for-key the HuggingFace
+``ViTForImageClassification`` the reference builds (reference start.py:258-267), so client
+checkpoints (``{'state_dict': ...}``, start.py:146-151) load unchanged.
+
+The module is a parameter container.  Its ``forward`` returns an object with ``.logits`` like
+HF's, computed by libsvit's batched forward with a single coalition (C = 1) -- it exists so
+that code written against ``net(img).logits`` (reference federated_learning/utils.py:886)
+keeps working; the utility loop itself never goes through nn.Module.forward.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+
+from ..layout import VitConfig, pack_state_dict, plan_layout, state_dict_spec, vit_preset
+
+
+class ViTForImageClassification(nn.Module):
+    def __init__(self, cfg: VitConfig, precision: str = "f16"):
+        super().__init__()
+        self.cfg = cfg
+        self.precision = precision
+        self._names = []
+        for key, shape in state_dict_spec(cfg):
+            p = nn.Parameter(torch.empty(shape, dtype=torch.float32), requires_grad=False)
+            self._register(key, p)
+        self.reset_parameters()
+        self._plan = None
+
+    # parameters are registered on nested holder modules so state_dict() yields HF's dotted keys
+    def _register(self, dotted: str, p: nn.Parameter) -> None:
+        mod: nn.Module = self
+        parts = dotted.split(".")
+        for name in parts[:-1]:
+            if not hasattr(mod, name):
+                mod.add_module(name, nn.Module())
+            mod = getattr(mod, name)
+        mod.register_parameter(parts[-1], p)
+        self._names.append(dotted)
+
+    @torch.no_grad()
+    def reset_parameters(self, std: float = 0.02, seed: Optional[int] = None) -> None:
+        """HF default init: N(0, initializer_range) weights, zero biases, unit LayerNorm."""
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        for name, p in self.named_parameters():
+            if name.endswith("bias"):
+                p.zero_()
+            elif "layernorm" in name and name.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+
+    @property
+    def config(self):  # a few HF-style attribute names
+        c = self.cfg
+        return SimpleNamespace(hidden_size=c.hidden, num_hidden_layers=c.layers, num_attention_heads=c.heads,
+                               intermediate_size=c.ff, image_size=c.image, patch_size=c.patch,
+                               num_channels=c.channels, num_labels=c.n_cls, layer_norm_eps=c.ln_eps)
+
+    @torch.no_grad()
+    def forward(self, pixel_values: torch.Tensor):
+        from .. import ops
+        from .._lib import PRECISIONS
+
+        if not pixel_values.is_cuda:
+            raise RuntimeError("ViTForImageClassification.forward runs on libsvit (CUDA, sm_100a) only")
+        dev = pixel_values.device
+        B = pixel_values.shape[0]
+        lay = plan_layout(self.cfg)
+        if self._plan is None or self._plan.max_images < B or self._plan.device != dev:
+            self._plan = ops.Plan(self.cfg, PRECISIONS[self.precision], 1, max(B, 1), dev)
+        plan = self._plan
+        row = pack_state_dict(lay, {k: v.detach() for k, v in self.state_dict().items()}).to(dev).unsqueeze(0)
+        one = torch.ones((1, 1), dtype=torch.float32, device=dev)
+        V = lay.vec_size
+        wvec = ops.aggregate(row[:, :V], None, one, out_dtype=torch.float32, P=V)
+        wmat = ops.aggregate(row[:, V:], None, one, out_dtype=plan.operand_dtype, P=lay.mat_size)
+        patches = plan.patchify(pixel_values.to(torch.float32))
+        logits = torch.empty((1, B, self.cfg.n_cls), dtype=torch.float32, device=dev)
+        plan.forward(wvec, wmat, patches, B, logits)
+        return SimpleNamespace(logits=logits[0])
+
+
+def infer_config(sd: Dict[str, torch.Tensor], heads: Optional[int] = None, ln_eps: float = 1e-12) -> VitConfig:
+    """Recover the geometry from an HF ViT state_dict (head count is not recoverable from
+    shapes; default = hidden / 64 as in every ViT-Ti/S/B/L)."""
+    def strip(k):
+        for pre in ("module.", "base_model.model."):
+            while k.startswith(pre):
+                k = k[len(pre):]
+        return k
+
+    sd = {strip(k): v for k, v in sd.items()}
+    proj = sd["vit.embeddings.patch_embeddings.projection.weight"]
+    hidden, channels, patch = proj.shape[0], proj.shape[1], proj.shape[2]
+    T = sd["vit.embeddings.position_embeddings"].shape[1]
+    side = int(round((T - 1) ** 0.5))
+    layers = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith("vit.encoder.layer."))
+    ff = sd["vit.encoder.layer.0.intermediate.dense.weight"].shape[0]
+    n_cls = sd["classifier.weight"].shape[0]
+    return VitConfig(hidden=hidden, layers=layers, heads=heads or max(1, hidden // 64), ff=ff, image=side * patch,
+                     n_cls=n_cls, patch=patch, channels=channels, ln_eps=ln_eps)
+
+
+def vit(name: str = "base", image: int = 224, n_cls: int = 4, **kw) -> ViTForImageClassification:
+    return ViTForImageClassification(vit_preset(name, image=image, n_cls=n_cls), **kw)

@@ -1,0 +1,45 @@
+"""Worker for test_dist_gloo.py: one rank of a world_size-2 gloo job on CPU."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch.distributed as td  # noqa: E402
+
+from helpers import synthetic_game  # noqa: E402
+from oracle import restate  # noqa: E402
+from oracle_evaluator import OracleEvaluator  # noqa: E402
+from shapley_vit_b200 import dist, estimators  # noqa: E402
+from shapley_vit_b200.fl import ClientBase, ServerBase  # noqa: E402
+from shapley_vit_b200.game import Game  # noqa: E402
+from shapley_vit_b200.synth import SizedStub  # noqa: E402
+
+
+def main():
+    out_path = sys.argv[1]
+    distributed = "RANK" in os.environ
+    if distributed:
+        td.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+    cfg, w0, _, deltas, n_train, images, labels = synthetic_game(n_clients=3, n_val=32, layers=1)
+    prev = list(restate.evaluation(w0, cfg, images, labels))
+    clients = [ClientBase(i, {}, None, SizedStub(n)) for i, n in enumerate(n_train)]
+    game = Game(clients, ServerBase({}, w0, clients, None, None, None), w0, deltas, [True] * 3, prev, 2, {})
+    game._evaluator = OracleEvaluator(cfg, w0, deltas, images, labels)
+    sv = estimators.shapley_exact(game)
+    rank, ws = dist.world()
+    res = dict(rank=rank, world=ws, evaluated_here=sum(game._evaluator.calls),
+               counts={",".join(map(str, sorted(k))): v for k, v in game.counts.items()},
+               sv=[[sv[d][c] for c in range(3)] for d in range(2)],
+               bounds=[dist.shard_bounds(7, r, ws) for r in range(ws)])
+    with open(out_path, "w") as f:
+        json.dump(res, f)
+    if distributed:
+        dist.barrier()
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

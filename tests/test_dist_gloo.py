@@ -1,0 +1,63 @@
+"""The N>1 path on CPU: world_size 2, gloo.  Coalitions are sharded across ranks, one all-gather
+brings the (correct, loss_sum) pairs back, and every rank ends with the same memo -- bit-identical
+to the single-process run."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def run_worker(tmp, rank=None, world=None, port=None):
+    env = dict(os.environ)
+    out = os.path.join(tmp, f"out_{rank}.json")
+    if rank is not None:
+        env.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   LOCAL_RANK=str(rank))
+    else:
+        for k in ("RANK", "WORLD_SIZE"):
+            env.pop(k, None)
+    env["OMP_NUM_THREADS"] = "2"
+    return subprocess.Popen([sys.executable, os.path.join(HERE, "_gloo_worker.py"), out], env=env), out
+
+
+def test_two_rank_gloo_matches_single_process(tmp_path):
+    tmp = str(tmp_path)
+    p0, single_out = run_worker(tmp)
+    assert p0.wait(timeout=600) == 0
+    single = json.load(open(single_out))
+    port = free_port()
+    procs = [run_worker(tmp, r, 2, port) for r in range(2)]
+    for p, _ in procs:
+        assert p.wait(timeout=600) == 0
+    ranks = [json.load(open(o)) for _, o in procs]
+    assert [r["world"] for r in ranks] == [2, 2]
+    # work was split: 7 coalitions -> 4 + 3
+    assert sorted(r["evaluated_here"] for r in ranks) == [3, 4]
+    assert single["evaluated_here"] == 7
+    for r in ranks:
+        assert r["counts"] == single["counts"]          # integer counts and fp64 loss sums, bit-identical
+        assert r["sv"] == single["sv"]
+    assert ranks[0]["bounds"] == [[0, 4], [4, 7]]
+
+
+def test_shard_bounds_cover_everything():
+    from shapley_vit_b200.dist import shard_bounds
+
+    for n in (0, 1, 7, 8, 255, 1023):
+        for ws in (1, 2, 4, 8):
+            got = []
+            for r in range(ws):
+                lo, hi = shard_bounds(n, r, ws)
+                got += list(range(lo, hi))
+            assert got == list(range(n))

@@ -1,0 +1,249 @@
+"""Per-kernel parity on the GPU, through the C ABI: K1 aggregation, K5 scoring, LayerNorm,
+attention, patchify and both GEMM back ends, each against the oracle / plain torch fp32 on the
+same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from shapley_vit_b200 import _lib, ops as _ops
+
+    sm, major, minor = _lib.device_info()
+    assert major == 10, "libsvit is sm_100a only"
+    return _ops
+
+
+def gen(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g, dtype=torch.float32) * scale
+
+
+# ----------------------------------------------------------------------------- K1
+def oracle_aggregate(deltas, w0, ratios):
+    """restate.get_aggregated_model + model_agg_lazy on flat fp32 rows (ascending members)."""
+    out = []
+    for row in ratios:
+        members = [j for j, r in enumerate(row) if r != 0]
+        agg = restate.get_aggregated_model([{"p": deltas[j]} for j in members], [float(row[j]) for j in members])
+        base = {"p": w0} if w0 is not None else {"p": torch.zeros_like(deltas[0])}
+        out.append(restate.model_agg_lazy(base, [agg] if agg is not None else [])["p"])
+    return torch.stack(out)
+
+
+def fedavg_rows(masks, n_train):
+    rows = []
+    for m in masks:
+        tot = sum(n for n, b in zip(n_train, m) if b)
+        rows.append([float(np.float32(n / tot)) if b else 0.0 for n, b in zip(n_train, m)])
+    return rows
+
+
+@pytest.mark.parametrize("N,C,P", [(1, 1, 8), (4, 15, 4096), (8, 32, 100_000), (8, 33, 33_333), (3, 5, 1027),
+                                   (16, 17, 70_001), (20, 9, 5_000), (40, 7, 3_000), (64, 3, 2_049)])
+def test_aggregate_fp32_bit_exact(ops, N, C, P):
+    rng = np.random.RandomState(N * 1000 + C)
+    stride = (P + 7) // 8 * 8
+    deltas = torch.zeros(N, stride)
+    deltas[:, :P] = gen(N, P, seed=P) * 0.02
+    w0 = torch.zeros(stride)
+    w0[:P] = gen(P, seed=P + 1) * 0.02
+    masks = [rng.rand(N) < 0.5 for _ in range(C)]
+    for m in masks:
+        if not m.any():
+            m[rng.randint(N)] = True
+    masks[0][:] = True
+    rows = fedavg_rows(masks, [1000 * (j + 1) for j in range(N)])
+    got = ops.aggregate(deltas.cuda(), w0.cuda(), torch.tensor(rows, dtype=torch.float32).cuda(), P=P).cpu()
+    want = oracle_aggregate(deltas[:, :P], w0[:P], rows)
+    assert torch.equal(got[:, :P], want)                       # bit-exact, no FMA contraction
+
+
+def test_aggregate_no_w0_and_identity(ops):
+    P = 10_000
+    deltas = gen(2, P, seed=3)
+    r = torch.tensor([[1.0, 0.0], [0.0, 1.0], [0.0, 0.0]])
+    got = ops.aggregate(deltas.cuda(), None, r.cuda()).cpu()
+    assert torch.equal(got[0], deltas[0]) and torch.equal(got[1], deltas[1])
+    assert torch.count_nonzero(got[2]) == 0                     # empty coalition: W0 (= 0) alone
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_aggregate_16bit_is_rounded_fp32_result(ops, dtype):
+    N, C, P = 8, 12, 50_000
+    deltas, w0 = gen(N, P, seed=5) * 0.02, gen(P, seed=6) * 0.02
+    rng = np.random.RandomState(0)
+    rows = fedavg_rows([rng.rand(N) < 0.6 for _ in range(C - 1)] + [np.ones(N, bool)], list(range(1, N + 1)))
+    r = torch.tensor(rows, dtype=torch.float32).cuda()
+    ref = ops.aggregate(deltas.cuda(), w0.cuda(), r)
+    got = ops.aggregate(deltas.cuda(), w0.cuda(), r, out_dtype=dtype)
+    assert torch.equal(got, ref.to(dtype))
+
+
+def test_aggregate_rejects_misaligned(ops):
+    from shapley_vit_b200._lib import SvitError
+
+    d = torch.zeros(2, 12, device="cuda")
+    with pytest.raises(SvitError):
+        ops.aggregate(d, None, torch.ones(1, 2, device="cuda"))        # stride 12 is not a multiple of 8
+
+
+# ----------------------------------------------------------------------------- K5
+@pytest.mark.parametrize("C,n,k", [(1, 1, 2), (3, 1000, 10), (8, 4097, 4), (2, 333, 1000)])
+def test_score_matches_torch(ops, C, n, k):
+    logits = gen(C, n, k, seed=n)
+    logits[0, 0, :] = 0.25                                              # all-equal row: first index wins
+    labels = torch.randint(0, k, (n,), generator=torch.Generator().manual_seed(1))
+    correct, loss, pred = ops.score(logits.cuda(), labels.cuda(), want_pred=True)
+    for c in range(C):
+        assert torch.equal(pred[c].cpu().long(), logits[c].argmax(dim=1))
+        assert int(correct[c]) == int((logits[c].argmax(dim=1) == labels).sum())
+        want = F.cross_entropy(logits[c].double(), labels, reduction="sum").item()
+        assert float(loss[c]) == pytest.approx(want, rel=2e-6, abs=1e-5)
+    c2, l2 = ops.score(logits.cuda(), labels.cuda(), correct.clone(), loss.clone(), accumulate=True)
+    assert torch.equal(c2, 2 * correct) and torch.allclose(l2, 2 * loss)
+
+
+def test_score_nan_propagates(ops):
+    logits = gen(1, 16, 5)
+    logits[0, 3, 2] = float("nan")
+    labels = torch.zeros(16, dtype=torch.int64)
+    _, loss = ops.score(logits.cuda(), labels.cuda())
+    assert torch.isnan(loss[0])
+
+
+# ----------------------------------------------------------------------------- LayerNorm / patchify / attention
+@pytest.mark.parametrize("h", [192, 384, 768, 1024])
+def test_layernorm(ops, h):
+    G, rows = 3, 197
+    x, g, b = gen(G, rows, h, seed=h) * 3 + 0.5, gen(G, h, seed=1) * 0.1 + 1, gen(G, h, seed=2) * 0.1
+    want = torch.stack([F.layer_norm(x[i], (h,), g[i], b[i], 1e-12) for i in range(G)])
+    got = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-12).cpu()
+    assert (got - want).abs().max() < 2e-5
+    for dt in (torch.bfloat16, torch.float16):
+        got = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-12, out_dtype=dt).cpu()
+        assert (got.float() - want).abs().max() < (4e-2 if dt == torch.bfloat16 else 5e-3)
+
+
+@pytest.mark.parametrize("image", [32, 224])
+def test_patchify(ops, image):
+    from shapley_vit_b200 import layout
+    from shapley_vit_b200._lib import PREC_F32
+
+    cfg = layout.vit_preset("tiny", image=image, n_cls=10, layers=1)
+    img = gen(5, 3, image, image, seed=image)
+    plan = ops.Plan(cfg, PREC_F32, 1, 5, "cuda:0")
+    got = plan.patchify(img.cuda()).cpu()
+    want = F.unfold(img, kernel_size=16, stride=16).transpose(1, 2).reshape(-1, 768)
+    assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("T,heads,d", [(5, 3, 64), (197, 12, 64), (197, 2, 32), (50, 2, 128)])
+def test_attention_fp32(ops, T, heads, d):
+    n_seq, h = 3, heads * d
+    qkv = gen(n_seq, T, 3 * h, seed=T)
+    q, k, v = (t.view(n_seq, T, heads, d).transpose(1, 2) for t in qkv.split(h, dim=2))
+    want = (torch.softmax(q @ k.transpose(2, 3) * d ** -0.5, dim=-1) @ v).transpose(1, 2).reshape(n_seq, T, h)
+    got = ops.attention(qkv.cuda(), heads).cpu()
+    assert (got - want).abs().max() < 2e-5
+    got16 = ops.attention(qkv.half().cuda(), heads).cpu().float()
+    assert (got16 - want).abs().max() < 5e-3
+
+
+# ----------------------------------------------------------------------------- GEMM
+def ref_gemm(A, B, bias=None, residual=None, gelu=False, rowvec=None, rows_in=0, rows_out=0, row_shift=0):
+    G = B.shape[0]
+    outs = []
+    for g in range(G):
+        a = A[g if A.shape[0] > 1 else 0].double()
+        y = a @ B[g].double().T
+        if bias is not None:
+            y = y + bias[g].double()
+        if gelu:
+            y = F.gelu(y)
+        if rows_in > 0:
+            M = y.shape[0]
+            full = torch.zeros((M // rows_in) * rows_out, y.shape[1], dtype=torch.float64)
+            idx = torch.arange(M)
+            orow = (idx // rows_in) * rows_out + row_shift + idx % rows_in
+            full[orow] = y + rowvec[g].double()[orow % rows_out]
+            y = full
+        if residual is not None:
+            y = y + residual[g].double()
+        outs.append(y)
+    return torch.stack(outs)
+
+
+@pytest.mark.parametrize("G,M,N,K", [(1, 64, 64, 64), (2, 200, 192, 192), (3, 130, 70, 96), (1, 1, 10, 768)])
+def test_gemm_cuda_core_fp32(ops, G, M, N, K):
+    from shapley_vit_b200._lib import PREC_F32
+
+    A, B, bias, res = gen(G, M, K, seed=1), gen(G, N, K, seed=2) * 0.05, gen(G, N, seed=3), gen(G, M, N, seed=4)
+    got = ops.gemm(PREC_F32, A.cuda(), B.cuda(), bias=bias.cuda(), residual=res.cuda(), gelu=True).cpu()
+    want = ref_gemm(A, B, bias, res, gelu=True)
+    assert (got.double() - want).abs().max() < 1e-4
+
+
+TC_SHAPES = [(1, 128, 256, 64), (1, 128, 128, 64), (2, 300, 768, 768), (3, 197 * 4, 2304, 768),
+             (2, 640, 192, 192), (2, 640, 576, 192), (1, 1000, 768, 3072), (2, 130, 384, 384)]
+
+
+@pytest.mark.parametrize("prec_name", ["f16", "bf16", "tf32"])
+@pytest.mark.parametrize("G,M,N,K", TC_SHAPES)
+def test_gemm_tcgen05_matches_cuda_core_gemm(ops, prec_name, G, M, N, K, monkeypatch):
+    """tcgen05 result == fp64 reference on the SAME rounded operands, to accumulation error."""
+    from shapley_vit_b200._lib import PRECISIONS
+
+    prec = PRECISIONS[prec_name]
+    dt = {"f16": torch.float16, "bf16": torch.bfloat16, "tf32": torch.float32}[prec_name]
+    A, B = gen(G, M, K, seed=M).to(dt), (gen(G, N, K, seed=N) * 0.05).to(dt)
+    bias, res = gen(G, N, seed=3), gen(G, M, N, seed=4)
+    got = ops.gemm(prec, A.cuda(), B.cuda(), bias=bias.cuda(), residual=res.cuda(), out_dtype=torch.float32).cpu()
+    if prec_name == "tf32":   # the tensor core truncates fp32 operands to 10 mantissa bits
+        want = ref_gemm(A, B, bias, res)
+        tol = 2e-3 * (K / 64) ** 0.5
+    else:
+        want = ref_gemm(A.float(), B.float(), bias, res)
+        tol = 1e-4 * (K / 64) ** 0.5
+    err = (got.double() - want).abs().max().item()
+    assert err < tol, f"max err {err}"
+
+
+@pytest.mark.parametrize("prec_name", ["f16", "tf32"])
+def test_gemm_tcgen05_epilogues(ops, prec_name):
+    from shapley_vit_b200._lib import PRECISIONS
+
+    prec = PRECISIONS[prec_name]
+    dt = torch.float16 if prec_name == "f16" else torch.float32
+    tol = 3e-3 if prec_name == "f16" else 6e-3
+    G, M, N, K = 2, 394, 768, 768
+    A, B, bias = gen(G, M, K, seed=7).to(dt), (gen(G, N, K, seed=8) * 0.05).to(dt), gen(G, N, seed=9)
+    # GELU, operand-dtype output
+    got = ops.gemm(prec, A.cuda(), B.cuda(), bias=bias.cuda(), gelu=True).cpu()
+    want = ref_gemm(A.float(), B.float(), bias, gelu=True)
+    assert (got.double() - want).abs().max() < tol
+    # shared A (group stride 0) + row remap + position add: the patch-embedding epilogue
+    np_, T = 196, 197
+    A1 = gen(1, 2 * np_, K, seed=10).to(dt)
+    pos = gen(G, T, N, seed=11)
+    out = torch.full((G, 2 * T, N), 7.0, device="cuda")
+    ops.gemm(prec, A1.cuda(), B.cuda(), bias=bias.cuda(), rowvec=pos.cuda(), rows_in=np_, rows_out=T, row_shift=1,
+             out_dtype=torch.float32, out=out)
+    want = ref_gemm(A1.float(), B.float(), bias, rowvec=pos, rows_in=np_, rows_out=T, row_shift=1)
+    got = out.cpu().double()
+    cls_rows = torch.tensor([0, T])
+    assert torch.all(got[:, cls_rows] == 7.0)                              # the [CLS] gap is untouched
+    mask = torch.ones(2 * T, dtype=torch.bool)
+    mask[cls_rows] = False
+    assert (got[:, mask] - want[:, mask]).abs().max() < tol
+    # in-place residual (out aliases residual), as the projection / MLP-down GEMMs run
+    X = gen(G, M, N, seed=12).cuda()
+    want = ref_gemm(A.float(), B.float(), bias, residual=X.cpu())
+    ops.gemm(prec, A.cuda(), B.cuda(), bias=bias.cuda(), residual=X, out_dtype=torch.float32, out=X)
+    assert (X.cpu().double() - want).abs().max() < tol
