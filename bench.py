@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""Benchmark of the client-contribution utility loop (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port + HF ViT)
+
+Workload (BASELINE config 2): 8-client FedAvg, ViT-B/16 at 224 px, 10 classes, 10 000-image
+synthetic validation set, exact-Shapley coalition enumeration (255 non-empty coalitions).
+A STEP is one batch of `--coalition-batch` coalitions per GPU taken from that enumeration:
+aggregate their weights (K1), run the batched ViT forward over the whole validation set (K2-K4)
+and score (K5).  metric = coalition utility evaluations per second, whole job (all ranks).
+
+Multi-GPU: one process per GPU (torchrun); rank 0 builds the stacked client deltas and W0 and
+NCCL-broadcasts them once; every rank evaluates its own coalition slice (weak scaling: per-GPU
+work per step is fixed); the timed region is bracketed by barrier + synchronize and the elapsed
+time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "coalition utility evals/sec (ViT-B/16, 8 clients)"
+UNIT = "coalition-evals/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--vit", default="base")
+    ap.add_argument("--image", type=int, default=224)
+    ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--clients", type=int, default=8)
+    ap.add_argument("--val", type=int, default=10000)
+    ap.add_argument("--coalition-batch", type=int, default=8)
+    ap.add_argument("--image-chunk", type=int, default=128)
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "tf32", "f32"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-images", type=int, default=48)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.clients}-client FedAvg ViT-{a.vit}/16 @{a.image}px, exact-Shapley enumeration "
+            f"({2 ** a.clients - 1} coalitions), {a.val}-image synthetic val set, {a.classes} classes "
+            f"(BASELINE config 2)")
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, 200 ms) -- started before and stopped after the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc, self.lines = None, []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's own path, restated (oracle/restate.py) around the
+# reference's actual third-party model (HF ViTForImageClassification, fp32 eager)
+# ----------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, a):
+        import torch
+
+        from oracle import restate
+        from oracle.hf_model import build_hf_vit
+        from shapley_vit_b200 import layout, synth
+
+        self.torch, self.restate = torch, restate
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.cores = torch.get_num_threads()
+        self.a = a
+        self.cfg = layout.vit_preset(a.vit, image=a.image, n_cls=a.classes)
+        self.w0 = synth.make_state_dict(self.cfg, a.seed)
+        clients = [synth.make_client_state_dict(self.w0, j, a.seed) for j in range(a.clients)]
+        self.deltas = [restate.get_difference_between_network_weights(sd, self.w0) for sd in clients]
+        del clients
+        self.n_train = synth.client_sizes(a.clients)
+        self.n_img = min(a.cpu_sample_images, a.val)
+        self.images, self.labels = synth.make_val_set(self.cfg, self.n_img, a.seed)
+        self.model = build_hf_vit(self.cfg, self.w0)
+        self.coalitions = list(restate.powerset(range(a.clients)))
+        self.sample = (f"1 coalition per step: full-size FedAvg aggregation + load_state_dict, forward/score on "
+                       f"{self.n_img} of {a.val} images (HF ViT fp32 eager, batch 128), extrapolated linearly in images")
+
+    def step(self, i: int) -> float:
+        """Seconds one full coalition evaluation would take (measured on the sample, extrapolated)."""
+        torch, restate = self.torch, self.restate
+        S = self.coalitions[(37 * i + len(self.coalitions) // 2) % len(self.coalitions)]
+        t0 = time.perf_counter()
+        members = restate.reference_member_order(S)
+        sd = restate.coalition_state_dict(self.w0, self.deltas, self.n_train, members)
+        self.model.load_state_dict(sd)
+        t_agg = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        correct, loss = 0, 0.0
+        for s in range(0, self.n_img, 128):                  # evaluation(), utils.py:864-926 (autograd on)
+            out = self.model(self.images[s:s + 128]).logits
+            pred = out.argmax(dim=1)
+            correct += pred.eq(self.labels[s:s + 128]).sum().item()
+            loss += torch.nn.functional.cross_entropy(out, self.labels[s:s + 128], reduction="sum").item()
+        t_fwd = time.perf_counter() - t0
+        return t_agg + t_fwd * (self.a.val / self.n_img)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu = CpuPath(a)
+    for i in range(a.warmup):
+        cpu.step(i)
+    t0 = time.perf_counter()
+    per = [cpu.step(a.warmup + i) for i in range(a.steps)]
+    wall = time.perf_counter() - t0
+    sec_per_eval = sum(per) / len(per)
+    value = 1.0 / sec_per_eval
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "step": "one coalition evaluation on a bounded sample, extrapolated",
+                   "device": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": cpu.sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+
+    from shapley_vit_b200 import _lib, dist, layout, ops, synth
+    from shapley_vit_b200.engine import CoalitionEngine, ValidationSet
+    from shapley_vit_b200.fl import ClientBase, ServerBase
+    from shapley_vit_b200.game import Game
+
+    rank = int(os.environ.get("RANK", "0"))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a B200 (there is no CPU path)")
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if ws > 1:
+        import torch.distributed as td
+
+        td.init_process_group("nccl", rank=rank, world_size=ws, device_id=dev)
+    _lib.device_info()
+
+    cfg = layout.vit_preset(a.vit, image=a.image, n_cls=a.classes)
+    lay = layout.plan_layout(cfg)
+    N, Cb = a.clients, a.coalition_batch
+    prec = _lib.PRECISIONS[a.precision]
+
+    # ---- client weights: built on rank 0, broadcast once over NVLink (NCCL) -------------------
+    deltas = torch.empty((N, lay.total), dtype=torch.float32, device=dev)
+    w0 = torch.empty(lay.total, dtype=torch.float32, device=dev)
+    if rank == 0:
+        w0_sd = synth.make_state_dict(cfg, a.seed)
+        w0.copy_(layout.pack_state_dict(lay, w0_sd))
+        row = torch.empty(lay.total, dtype=torch.float32).pin_memory()
+        for j in range(N):
+            cj = synth.make_client_state_dict(w0_sd, j, a.seed)
+            layout.pack_state_dict(lay, {k: cj[k] - w0_sd[k] for k in cj}, out=row)   # F1: delta_j = W_j - W_0
+            deltas[j].copy_(row)
+        del w0_sd
+    dist.broadcast_(deltas)
+    dist.broadcast_(w0)
+
+    # ---- validation set: replicated (same seed on every rank), host copy kept for the e2e leg --
+    g = torch.Generator(device=dev).manual_seed(a.seed + 424243)
+    try:
+        images_host = torch.empty((a.val, cfg.channels, cfg.image, cfg.image), dtype=torch.float32).pin_memory()
+    except RuntimeError:
+        images_host = torch.empty((a.val, cfg.channels, cfg.image, cfg.image), dtype=torch.float32)
+    for s in range(0, a.val, 1000):
+        n = min(1000, a.val - s)
+        images_host[s:s + n].copy_(torch.randn((n, cfg.channels, cfg.image, cfg.image), generator=g, device=dev))
+    labels_host = torch.randint(0, cfg.n_cls, (a.val,), generator=g, device=dev).cpu()
+    val = ValidationSet(cfg, images_host, labels_host, prec, dev)
+    eng = CoalitionEngine(cfg, w0, deltas, val, precision=prec, coalition_batch=Cb, image_chunk=a.image_chunk,
+                          device=dev)
+    eng.profile = True
+
+    # ---- coalition enumeration (exact Shapley order), FedAvg ratio rows -----------------------
+    from shapley_vit_b200.estimators import powerset
+
+    n_train = synth.client_sizes(N)
+    coalitions = list(powerset(range(N)))
+    clients = [ClientBase(i, {}, None, synth.SizedStub(n)) for i, n in enumerate(n_train)]
+    server = ServerBase({}, None, clients, None, val, None)
+
+    def rows_for(step: int, r: int):
+        out = []
+        for q in range(Cb):
+            S = coalitions[((step * ws + r) * Cb + q) % len(coalitions)]
+            ratio = server.get_agg_ratio(selected_clients=[clients[j] for j in S])
+            row = [0.0] * N
+            for j, v in zip(S, ratio):
+                row[j] = v
+            out.append(row)
+        return out
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for i in range(a.warmup):
+        eng.evaluate(rows_for(i, rank))
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+
+    # ---- timed region: K steps, inputs resident in HBM ----------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    eng.kernel_launches = 0
+    eng.agg_spans.clear()
+    eng.plan.timing_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    ev0.record()
+    results = [eng._run_batch(rows_for(a.warmup + i, rank)) for i in range(a.steps)]
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    timing = eng.plan.timing_end()
+    launches = eng.kernel_launches
+    agg_ms = sum(s.elapsed_time(e) for s, e in eng.agg_spans)
+    agg_launches = len(eng.agg_spans)
+    for c, l in results:
+        assert not torch.isnan(l).any(), "loss is nan"
+    if ws > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = a.steps * Cb * ws / (elapsed_ms / 1e3)
+
+    # ---- e2e: the public API (Game.eval_utilities) with HOST buffers every step ---------------
+    e2e = None
+    if not a.no_e2e:
+        game = Game(clients, server, None, [None] * N, [True] * N, [0.0, 0.0], 2, {"precision": a.precision})
+        game._engine = eng
+        per_rank = Cb
+
+        def e2e_step(i: int):
+            h2d = val.upload(images_host, labels_host)          # validation images + labels, host -> device
+            todo = [coalitions[((i * ws + r) * per_rank + q) % len(coalitions)] for r in range(ws) for q in range(per_rank)]
+            game.utility = [{}, {}]
+            game.eval_utilities(todo)                           # ratios H2D, (correct, loss) D2H inside
+            return h2d + eng.upload_bytes_per_batch(), per_rank * 16
+
+        e2e_step(0)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(a.steps):
+            h2d_b, d2h_b = e2e_step(a.warmup + i)
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        if ws > 1:
+            t = torch.tensor([wall], dtype=torch.float64, device=dev)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            wall = float(t.item())
+        e2e = {"value": a.steps * Cb * ws / wall, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b),
+               "d2h_bytes_per_step": int(d2h_b),
+               "note": "per step: validation images+labels re-uploaded from pinned host memory and patchified, "
+                       "ratio rows H2D, per-coalition (correct, loss_sum) D2H; client deltas/W0 stay resident"}
+
+    if rank != 0:
+        if ws > 1:
+            td.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the tcgen05 grouped GEMM) ---------------------------
+    peaks, peak_src = load_peaks()
+    g_ms, g_flops, g_n = timing["gemm"]
+    tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 grouped GEMM)" if a.precision != "f32" else "gemm_simt_kernel",
+                "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+                "peak_source": f"{peak_src}; sustained figure (kernel timed inside a long step); burst = {peaks['bf16_tflops']}",
+                "traffic": None, "launches": int(g_n), "avg_launch_ms": g_ms / max(g_n, 1),
+                "share_of_step": g_ms / elapsed_ms}
+    a_ms, a_flops, a_n = timing["attention"]
+    l_ms, l_bytes, l_n = timing["layernorm"]
+    es = 2 if a.precision in ("f16", "bf16") else 4
+    agg_bytes = a.steps * (4.0 * lay.total * (N + 1) + (4.0 * lay.vec_size + es * lay.mat_size) * Cb)
+    breakdown = {
+        "gemm_ms": g_ms, "attention_ms": a_ms, "attention_tflops": a_flops / (a_ms / 1e3) / 1e12 if a_ms else None,
+        "layernorm_ms": l_ms, "layernorm_gbs": l_bytes / (l_ms / 1e3) / 1e9 if l_ms else None,
+        "aggregate_ms": agg_ms, "forward_ms": timing["forward"][0], "step_ms_total": elapsed_ms,
+    }
+    roofline_agg = {"bound": "hbm", "kernel": "aggregate_kernel (K1)", "achieved": agg_bytes / (agg_ms / 1e3) / 1e9 if agg_ms else None,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "launches": agg_launches,
+                    "frac": (agg_bytes / (agg_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if agg_ms else None,
+                    "algorithmic_bytes_per_step": agg_bytes / a.steps}
+    model_flops = cfg.flops_per_image() * a.val * Cb * a.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": a.precision, "data": "synthetic",
+        "config": {"workload": workload_name(a), "step": f"{Cb} coalitions per GPU: aggregate + forward over {a.val} images + score",
+                   "coalition_batch": Cb, "image_chunk": a.image_chunk, "parallelism": f"coalition-sharded x{ws}",
+                   "l2": "inputs per step (2.7 GB delta stack, 3 GB patch matrix) exceed the 126 MB L2; no flush needed",
+                   "model_tflops_per_s_per_gpu": model_flops / (elapsed_ms / 1e3) / 1e12},
+        "roofline": roofline, "roofline_aggregate": roofline_agg, "breakdown": breakdown,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if ws == 1 and not a.no_cpu_baseline:
+        cpu = CpuPath(a)
+        cpu.step(0)
+        t0, per = time.perf_counter(), []
+        i = 1
+        while time.perf_counter() - t0 < 12.0 and i < 4:
+            per.append(cpu.step(i))
+            i += 1
+        sec = sum(per) / len(per)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": cpu.sample}
+    print(json.dumps(line), flush=True)
+    if ws > 1:
+        td.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,8 @@
  *                            (HF ViTForImageClassification built at start.py:258-267)
  *   svit_score            <- argmax / correct / CrossEntropy(sum) in evaluation,
  *                            federated_learning/utils.py:891-894
+ *   svit_plan_timing_*    <- (new) CUDA-event timing per kernel class; the reference only prints
+ *                            'before net' / 'after net' (federated_learning/utils.py:885-887)
  *   svit_gemm, svit_layernorm, svit_attention
  *                         <- the ATen/cuBLAS calls the HF forward issues per layer; exported so
  *                            each kernel can be parity-tested and timed in isolation
@@ -129,6 +131,20 @@ int svit_patchify(const svit_plan* plan, const float* images, void* patches, int
 int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat,
                          int64_t mat_stride, const void* patches, float* logits, int64_t logits_stride,
                          int C, int B, void* workspace, size_t workspace_bytes, svit_stream_t stream);
+
+/* Device-side timing of the forward by kernel class, for roofline reporting: between _begin and
+ * _end every launch of svit_forward_batched on this plan is bracketed by CUDA events on its
+ * stream; _end waits for them and returns, per class, the summed duration, the summed
+ * algorithmic work (FLOPs for GEMM and attention, bytes for LayerNorm) and the launch count.
+ * SVIT_CLS_FORWARD spans whole svit_forward_batched calls. */
+enum svit_kernel_class { SVIT_CLS_GEMM = 0, SVIT_CLS_ATTENTION, SVIT_CLS_LAYERNORM, SVIT_CLS_FORWARD, SVIT_CLS_COUNT };
+typedef struct svit_timing {
+  double ms[SVIT_CLS_COUNT];
+  double work[SVIT_CLS_COUNT];
+  int64_t launches[SVIT_CLS_COUNT];
+} svit_timing;
+int svit_plan_timing_begin(svit_plan* plan);
+int svit_plan_timing_end(svit_plan* plan, svit_timing* out);
 
 /* ---- K5: scoring ---------------------------------------------------------------------
  * For each coalition c: correct[c] (+)= #{i : argmax_k logits[c,i,k] == labels[i]} (first maximal

@@ -23,8 +23,9 @@ EXPORTS = [
     "svit_version", "svit_last_error", "svit_device_info", "svit_layout_sizes", "svit_layout_segment",
     "svit_aggregate", "svit_plan_create", "svit_plan_destroy", "svit_plan_workspace_bytes",
     "svit_plan_operand_dtype", "svit_patchify", "svit_forward_batched", "svit_score", "svit_gemm",
-    "svit_layernorm", "svit_attention",
+    "svit_layernorm", "svit_attention", "svit_plan_timing_begin", "svit_plan_timing_end",
 ]
+KERNEL_CLASSES = ("gemm", "attention", "layernorm", "forward")
 
 
 class SvitError(RuntimeError):
@@ -41,6 +42,10 @@ class VitCfgC(C.Structure):
 class SegmentC(C.Structure):
     _fields_ = [("kind", C.c_int32), ("layer", C.c_int32), ("region", C.c_int32), ("reserved", C.c_int32),
                 ("offset", C.c_int64), ("size", C.c_int64), ("rows", C.c_int64), ("cols", C.c_int64)]
+
+
+class TimingC(C.Structure):
+    _fields_ = [("ms", C.c_double * 4), ("work", C.c_double * 4), ("launches", C.c_int64 * 4)]
 
 
 class EpilogueC(C.Structure):
@@ -89,6 +94,8 @@ def load() -> C.CDLL:
         "svit_gemm": (i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, C.POINTER(EpilogueC), vp]),
         "svit_layernorm": (i32, [vp, i64, i64, vp, vp, i64, vp, i64, i64, i32, i32, i64, i32, f32, vp]),
         "svit_attention": (i32, [vp, vp, i32, i64, i32, i32, i32, vp]),
+        "svit_plan_timing_begin": (i32, [vp]),
+        "svit_plan_timing_end": (i32, [vp, C.POINTER(TimingC)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch; let it propagate

@@ -20,6 +20,7 @@
 // row gap.  The head (final LN on CLS + classifier) is one fp32 warp per (coalition, image).
 #include <cstdlib>
 #include <new>
+#include <vector>
 
 #include "elementwise.h"
 #include "epilogue.cuh"
@@ -33,6 +34,16 @@ struct svit_plan {
   bool force_simt = false;
   // workspace byte offsets for (max_c, max_b)
   size_t off_x = 0, off_xn = 0, off_qkv = 0, off_ctx = 0, off_h = 0, ws_bytes = 0;
+  // optional per-kernel-class device timing (svit_plan_timing_begin / _end)
+  bool timing = false;
+  struct Span {
+    cudaEvent_t a, b;
+    int cls;
+    double work;  // flops (GEMM, attention) or bytes (others)
+  };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> pool;
+  size_t pool_used = 0;
 };
 
 namespace svit {
@@ -48,8 +59,38 @@ int operand_dtype_of(int precision) {
   }
 }
 
-int gemm_dispatch(const svit_plan* p, const void* A, int64_t a_gs, const void* B, int64_t b_gs, int G, int M, int N,
+cudaEvent_t take_event(svit_plan* p) {
+  if (p->pool_used == p->pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    p->pool.push_back(e);
+  }
+  return p->pool[p->pool_used++];
+}
+
+// RAII span: records an event pair around the launches issued in its scope when timing is on
+struct Timed {
+  svit_plan* p;
+  cudaStream_t s;
+  svit_plan::Span span;
+  Timed(svit_plan* plan, cudaStream_t stream, int cls, double work) : p(plan), s(stream) {
+    if (!p->timing) return;
+    span.a = take_event(p);
+    span.b = take_event(p);
+    span.cls = cls;
+    span.work = work;
+    cudaEventRecord(span.a, s);
+  }
+  ~Timed() {
+    if (!p->timing) return;
+    cudaEventRecord(span.b, s);
+    p->spans.push_back(span);
+  }
+};
+
+int gemm_dispatch(svit_plan* p, const void* A, int64_t a_gs, const void* B, int64_t b_gs, int G, int M, int N,
                   int K, const EpiArgs& epi, cudaStream_t stream) {
+  Timed t(p, stream, SVIT_CLS_GEMM, 2.0 * G * M * (double)N * K);
   if (p->precision == SVIT_PREC_F32 || p->force_simt)
     return gemm_simt(p->operand_dtype, A, a_gs, B, b_gs, G, M, N, K, epi, stream);
   return gemm_tc(p->precision, A, a_gs, B, b_gs, G, M, N, K, epi, stream);
@@ -105,6 +146,8 @@ extern "C" int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_
 }
 
 extern "C" int svit_plan_destroy(svit_plan* plan) {
+  if (plan)
+    for (cudaEvent_t e : plan->pool) cudaEventDestroy(e);
   delete plan;
   return SVIT_OK;
 }
@@ -156,6 +199,7 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
   int rc;
 
   // ---- embeddings ----
+  Timed whole(plan, stream, SVIT_CLS_FORWARD, 0.0);
   if ((rc = embed_cls(X, xgs, wvec, vec_stride, L.find(SVIT_SEG_CLS), L.find(SVIT_SEG_POS), C, B, T, h, stream))) return rc;
   {
     svit_epilogue e{};
@@ -171,9 +215,12 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
   }
   // ---- encoder ----
   for (int l = 0; l < cfg.layers; ++l) {
-    if ((rc = layernorm(X, xgs, h, vec(SVIT_SEG_LN1_G, l), vec(SVIT_SEG_LN1_B, l), vec_stride, Xn, xgs, h, odt, C, M, h,
-                        cfg.ln_eps, stream)))
-      return rc;
+    {
+      Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * M * h * (4.0 + es));
+      if ((rc = layernorm(X, xgs, h, vec(SVIT_SEG_LN1_G, l), vec(SVIT_SEG_LN1_B, l), vec_stride, Xn, xgs, h, odt, C, M, h,
+                          cfg.ln_eps, stream)))
+        return rc;
+    }
     {
       svit_epilogue e{};
       e.bias = vec(SVIT_SEG_BQ, l);  // bq | bk | bv are contiguous
@@ -181,7 +228,10 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       EpiArgs ea = make_epi(&e, QKV, (int64_t)M * 3 * h, odt, M, 3 * h);
       if ((rc = gemm_dispatch(plan, Xn, xgs, mat(SVIT_SEG_WQ, l), mat_stride, C, M, 3 * h, h, ea, stream))) return rc;
     }
-    if ((rc = attention(QKV, CTX, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream))) return rc;
+    {
+      Timed t(plan, stream, SVIT_CLS_ATTENTION, 4.0 * C * B * (double)T * T * h);
+      if ((rc = attention(QKV, CTX, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream))) return rc;
+    }
     {
       svit_epilogue e{};
       e.bias = vec(SVIT_SEG_BO, l);
@@ -191,9 +241,12 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, M, h);
       if ((rc = gemm_dispatch(plan, CTX, xgs, mat(SVIT_SEG_WO, l), mat_stride, C, M, h, h, ea, stream))) return rc;
     }
-    if ((rc = layernorm(X, xgs, h, vec(SVIT_SEG_LN2_G, l), vec(SVIT_SEG_LN2_B, l), vec_stride, Xn, xgs, h, odt, C, M, h,
-                        cfg.ln_eps, stream)))
-      return rc;
+    {
+      Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * M * h * (4.0 + es));
+      if ((rc = layernorm(X, xgs, h, vec(SVIT_SEG_LN2_G, l), vec(SVIT_SEG_LN2_B, l), vec_stride, Xn, xgs, h, odt, C, M, h,
+                          cfg.ln_eps, stream)))
+        return rc;
+    }
     {
       svit_epilogue e{};
       e.bias = vec(SVIT_SEG_B1, l);
@@ -231,4 +284,31 @@ extern "C" int svit_gemm(int precision, const void* A, int64_t a_gs, const void*
   if (precision == SVIT_PREC_F32 || (env && env[0] == '1'))
     return gemm_simt(odt, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
   return gemm_tc(precision, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int svit_plan_timing_begin(svit_plan* plan) {
+  using namespace svit;
+  SVIT_CHECK_ARG(plan != nullptr, "svit_plan_timing_begin: plan is null");
+  plan->timing = true;
+  plan->spans.clear();
+  plan->pool_used = 0;
+  return SVIT_OK;
+}
+
+extern "C" int svit_plan_timing_end(svit_plan* plan, svit_timing* out) {
+  using namespace svit;
+  SVIT_CHECK_ARG(plan && out, "svit_plan_timing_end: null pointer");
+  plan->timing = false;
+  for (int c = 0; c < SVIT_CLS_COUNT; ++c) out->ms[c] = 0.0, out->work[c] = 0.0, out->launches[c] = 0;
+  for (const auto& sp : plan->spans) {
+    SVIT_CUDA(cudaEventSynchronize(sp.b));
+    float ms = 0.f;
+    SVIT_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+    out->ms[sp.cls] += ms;
+    out->work[sp.cls] += sp.work;
+    out->launches[sp.cls] += 1;
+  }
+  plan->spans.clear();
+  plan->pool_used = 0;
+  return SVIT_OK;
 }

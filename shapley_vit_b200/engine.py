@@ -78,8 +78,7 @@ class ValidationSet:
 
 
 class CoalitionEngine:
-    def __init__(self, cfg: VitConfig, w0: Optional[Dict[str, torch.Tensor]],
-                 deltas: Sequence[Dict[str, torch.Tensor]], images, labels: Optional[torch.Tensor] = None,
+    def __init__(self, cfg: VitConfig, w0, deltas, images, labels: Optional[torch.Tensor] = None,
                  precision: str = "f16", coalition_batch: int = 8, image_chunk: int = 128,
                  device: str | torch.device = "cuda:0", keep_logits: bool = False):
         """``images`` is either a host tensor [n, C, H, W] (with ``labels``) or a ValidationSet."""
@@ -89,7 +88,7 @@ class CoalitionEngine:
         self.device = torch.device(device)
         self.lay: PlanLayout = plan_layout(cfg)
         self.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
-        self.n_clients = len(deltas)
+        self.n_clients = int(deltas.shape[0]) if isinstance(deltas, torch.Tensor) else len(deltas)
         if not 1 <= self.n_clients <= 64:
             raise ValueError("1..64 clients supported")
         self.n_val = images.n if isinstance(images, ValidationSet) else int(images.shape[0])
@@ -98,15 +97,25 @@ class CoalitionEngine:
         self.keep_logits = keep_logits
         self.last_logits: Optional[torch.Tensor] = None
         self.kernel_launches = 0
+        self.profile = False                      # bench.py: CUDA-event pairs around the K1 launches
+        self.agg_spans: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
         with torch.cuda.device(self.device):
             self.plan = ops.Plan(cfg, self.precision, self.coalition_batch, self.image_chunk, self.device)
             total = self.lay.total
-            # stacked deltas [N, total] and W0 [total], plan layout, fp32, resident
-            host = torch.empty((self.n_clients, total), dtype=torch.float32, pin_memory=True)
-            for j, d in enumerate(deltas):
-                pack_state_dict(self.lay, d, out=host[j])
-            self.deltas = host.to(self.device, non_blocking=True)
-            if w0 is not None:
+            # stacked deltas [N, total] and W0 [total], plan layout, fp32, resident.  Already
+            # packed tensors (e.g. received by NCCL broadcast) are taken as they are.
+            if isinstance(deltas, torch.Tensor):
+                if deltas.shape != (self.n_clients, total) or deltas.dtype != torch.float32:
+                    raise ValueError(f"packed deltas must be fp32 [N, {total}]")
+                self.deltas = deltas.to(self.device).contiguous()
+            else:
+                host = torch.empty((self.n_clients, total), dtype=torch.float32, pin_memory=True)
+                for j, d in enumerate(deltas):
+                    pack_state_dict(self.lay, d, out=host[j])
+                self.deltas = host.to(self.device, non_blocking=True)
+            if isinstance(w0, torch.Tensor):
+                self.w0 = w0.to(self.device, dtype=torch.float32).contiguous()
+            elif w0 is not None:
                 self.w0 = pack_state_dict(self.lay, w0).to(self.device)
             else:
                 self.w0 = None
@@ -154,8 +163,14 @@ class CoalitionEngine:
         V, Mz = lay.vec_size, lay.mat_size
         w0v = self.w0[:V] if self.w0 is not None else None
         w0m = self.w0[V:] if self.w0 is not None else None
+        if self.profile:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         ops.aggregate(self.deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
         ops.aggregate(self.deltas[:, V:], w0m, ratios, out=self.wmat[:Cn], P=Mz)
+        if self.profile:
+            e1.record()
+            self.agg_spans.append((e0, e1))
         logits = self.logits[:Cn]
         npch = cfg.n_patches
         for s in range(0, self.n_val, self.image_chunk):

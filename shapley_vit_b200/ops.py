@@ -160,6 +160,15 @@ class Plan:
         except Exception:
             pass
 
+    def timing_begin(self) -> None:
+        check(_lib.load().svit_plan_timing_begin(self._h))
+
+    def timing_end(self):
+        """{class: (ms, work, launches)} accumulated since timing_begin (synchronises)."""
+        t = _lib.TimingC()
+        check(_lib.load().svit_plan_timing_end(self._h, C.byref(t)))
+        return {name: (t.ms[i], t.work[i], t.launches[i]) for i, name in enumerate(_lib.KERNEL_CLASSES)}
+
     def patchify(self, images: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         _cuda(images, "images", torch.float32)
         images = images.contiguous()
