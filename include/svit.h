@@ -99,7 +99,8 @@ int svit_layout_segment(const svit_vit_cfg* cfg, int32_t index, svit_segment* ou
  * arithmetic of get_aggregated_model followed by model_agg_lazy.  The [N, P] stack is read
  * from HBM ONCE for all C coalitions.
  *   deltas  device [N, delta_stride] fp32     w0   device [P] fp32 (NULL = zeros)
- *   ratios  device [C, N] fp32, 0 for non-members (FedAvg n_j / sum n over the coalition)
+ *   ratios  HOST   [C, N] fp32, 0 for non-members (FedAvg n_j / sum n over the coalition); they are
+ *           copied into the kernel parameters at launch, the caller may reuse the buffer at once
  *   out     device [C, out_stride] of out_dtype (SVIT_F32 / SVIT_BF16 / SVIT_F16)
  * Requirements: deltas, w0, out 16-byte aligned; delta_stride and out_stride multiples of 8
  * and >= P rounded up to 8; 1 <= N <= 64; 1 <= C <= 256. */

@@ -1,0 +1,17 @@
+#!/bin/bash
+# ncu evidence for the bench command (reduced validation set so the launch list stays short).
+# Usage: bash scripts/gpu_profile.sh <tag>      -> gpurun_out/<tag>_*.{csv,ncu-rep,log}
+TAG=${1:-r01}
+mkdir -p gpurun_out
+CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --val 1024"
+$CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
+tail -1 gpurun_out/${TAG}_plain.log | cut -c1-400
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
+echo "launch list rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 30 -c 4 -o gpurun_out/${TAG}_gemm -f $CMD > gpurun_out/${TAG}_ncu_gemm.log 2>&1
+echo "gemm full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:aggregate_kernel -c 4 -o gpurun_out/${TAG}_aggregate -f $CMD > gpurun_out/${TAG}_ncu_agg.log 2>&1
+echo "aggregate full rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:attention_mma_kernel -s 4 -c 2 -o gpurun_out/${TAG}_attention -f $CMD > gpurun_out/${TAG}_ncu_att.log 2>&1
+echo "attention full rc=$?"
+ls -la gpurun_out/

@@ -24,7 +24,9 @@
 namespace svit {
 namespace {
 
-constexpr int kCChunk = 16;  // coalition accumulators held in registers per pass
+constexpr int kCChunk = 8;      // coalition accumulators held in registers per pass
+constexpr int kVec = 8;         // consecutive parameters per thread
+constexpr int kMaxRatios = 2048;  // C * N floats travelling as kernel parameters per launch
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -49,8 +51,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // bounded: a lost TMA completion traps instead of hanging the GPU
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
-    if (spin > (1u << 26)) __trap();
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -60,27 +64,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
+// 4 consecutive outputs, one streaming vector store (8 bytes for fp16/bf16, 16 for fp32)
 template <typename OutT> struct Store4;
 template <> struct Store4<float> {
-  static __device__ __forceinline__ void st(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+  static __device__ __forceinline__ void st(float* p, const float* v) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
 };
 template <> struct Store4<__nv_bfloat16> {
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&lo);
-    u.y = *reinterpret_cast<uint32_t*>(&hi);
-    __stcs(reinterpret_cast<uint2*>(p), u);
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3])));
   }
 };
 template <> struct Store4<__half> {
-  static __device__ __forceinline__ void st(__half* p, float4 v) {
-    __half2 lo = __halves2half2(Cvt<__half>::from_f(v.x), Cvt<__half>::from_f(v.y));
-    __half2 hi = __halves2half2(Cvt<__half>::from_f(v.z), Cvt<__half>::from_f(v.w));
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&lo);
-    u.y = *reinterpret_cast<uint32_t*>(&hi);
-    __stcs(reinterpret_cast<uint2*>(p), u);
+  static __device__ __forceinline__ void st(__half* p, const float* v) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3])));
   }
 };
 
@@ -88,27 +86,27 @@ struct AggParams {
   const float* deltas;
   int64_t delta_stride;
   const float* w0;  // may be null
-  const float* ratios;
   void* out;
   int64_t out_stride;
   int64_t P;
   int N, C, stages;
   int64_t num_tiles;
+  // FedAvg ratios [C, N], by value: they reach the SM through the constant bank, so the
+  // membership test (ratio != 0) and the multiplier are warp-uniform operands, not loads.
+  float ratios[kMaxRatios];
 };
 
-// dynamic smem: [STAGES][(N+1)][TILE] floats | ratios [C*N] floats | mbarriers [STAGES]
+// dynamic smem: [STAGES][(N+1)][TILE] floats | mbarriers [STAGES]
 template <typename OutT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) aggregate_kernel(const AggParams p) {
-  constexpr int TILE = BLOCK * 4;
+__global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant__ AggParams p) {
+  constexpr int TILE = BLOCK * kVec;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.N, C = p.C, S = p.stages;
   const int rows = N + 1;  // row N holds W_0
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  float* s_ratio = stage_base + (size_t)S * rows * TILE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ratio + (((size_t)C * N + 1) & ~(size_t)1));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)S * rows * TILE);
   const int tid = threadIdx.x;
 
-  for (int i = tid; i < C * N; i += BLOCK) s_ratio[i] = p.ratios[i];
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -150,25 +148,40 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const AggParams p) {
     } else {
       mbar_wait(&bars[s], parity);
     }
-    const int e0 = tid * 4;
-    if (e0 < len) {
-      const float4 w = p.w0 ? *reinterpret_cast<const float4*>(st + (size_t)N * TILE + e0) : make_float4(0, 0, 0, 0);
-      OutT* outp = reinterpret_cast<OutT*>(p.out) + t * TILE + e0;
-      for (int c0 = 0; c0 < C; c0 += kCChunk) {
-        float4 acc[kCChunk];
+    // Each thread owns two groups of 4 consecutive parameters, TILE/2 apart, so that every
+    // 128-bit shared-memory read of a warp is contiguous (conflict-free).
+    const int ea = tid * 4, eb = TILE / 2 + tid * 4;
+    if (ea < len) {
+      const bool has_b = eb < len;
+      float w[kVec];
 #pragma unroll
-        for (int cc = 0; cc < kCChunk; ++cc) acc[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < kVec; ++q) w[q] = 0.f;
+      if (p.w0) {
+        const float4 a = *reinterpret_cast<const float4*>(st + (size_t)N * TILE + ea);
+        w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w;
+        if (has_b) {
+          const float4 b = *reinterpret_cast<const float4*>(st + (size_t)N * TILE + eb);
+          w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
+        }
+      }
+      OutT* outp = reinterpret_cast<OutT*>(p.out) + t * TILE;
+      for (int c0 = 0; c0 < C; c0 += kCChunk) {
+        float acc[kCChunk][kVec];
+#pragma unroll
+        for (int cc = 0; cc < kCChunk; ++cc)
+#pragma unroll
+          for (int q = 0; q < kVec; ++q) acc[cc][q] = 0.f;
         for (int j = 0; j < N; ++j) {
-          const float4 d = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + e0);
+          const float4 da = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + ea);
+          const float4 db = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + eb);
+          const float d[kVec] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
           for (int cc = 0; cc < kCChunk; ++cc) {
             if (c0 + cc < C) {
-              const float r = s_ratio[(c0 + cc) * N + j];  // warp-uniform broadcast read
+              const float r = p.ratios[(c0 + cc) * N + j];  // constant bank, warp-uniform
               if (r != 0.f) {
-                acc[cc].x = __fadd_rn(acc[cc].x, __fmul_rn(r, d.x));
-                acc[cc].y = __fadd_rn(acc[cc].y, __fmul_rn(r, d.y));
-                acc[cc].z = __fadd_rn(acc[cc].z, __fmul_rn(r, d.z));
-                acc[cc].w = __fadd_rn(acc[cc].w, __fmul_rn(r, d.w));
+#pragma unroll
+                for (int q = 0; q < kVec; ++q) acc[cc][q] = __fadd_rn(acc[cc][q], __fmul_rn(r, d[q]));
               }
             }
           }
@@ -176,17 +189,20 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const AggParams p) {
 #pragma unroll
         for (int cc = 0; cc < kCChunk; ++cc) {
           if (c0 + cc < C) {
-            float4 v;
-            v.x = __fadd_rn(w.x, acc[cc].x);
-            v.y = __fadd_rn(w.y, acc[cc].y);
-            v.z = __fadd_rn(w.z, acc[cc].z);
-            v.w = __fadd_rn(w.w, acc[cc].w);
+            float v[kVec];
+#pragma unroll
+            for (int q = 0; q < kVec; ++q) v[q] = __fadd_rn(w[q], acc[cc][q]);
             OutT* o = outp + (size_t)(c0 + cc) * p.out_stride;
-            if (e0 + 4 <= len) {
-              Store4<OutT>::st(o, v);
-            } else {  // ragged tail: element-wise
-              const float vv[4] = {v.x, v.y, v.z, v.w};
-              for (int q = 0; q < 4 && e0 + q < len; ++q) o[q] = Cvt<OutT>::from_f(vv[q]);
+#pragma unroll
+            for (int grp = 0; grp < 2; ++grp) {
+              const int e = grp ? eb : ea;
+              if (e + 4 <= len) {
+                Store4<OutT>::st(o + e, v + 4 * grp);
+              } else {  // ragged tail: element-wise
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (e + q < len) o[e + q] = Cvt<OutT>::from_f(v[4 * grp + q]);
+              }
             }
           }
         }
@@ -207,21 +223,20 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const AggParams p) {
 template <typename OutT, int BLOCK>
 int launch(const AggParams& base, cudaStream_t stream) {
   AggParams p = base;
-  constexpr int TILE = BLOCK * 4;
+  constexpr int TILE = BLOCK * kVec;
   p.num_tiles = (p.P + TILE - 1) / TILE;
   const size_t stage_bytes = (size_t)(p.N + 1) * TILE * 4;
-  const size_t fixed = ((((size_t)p.C * p.N + 1) & ~(size_t)1) * 4) + 8 * 8;
+  const size_t fixed = 8 * 8;
   const size_t budget = 227 * 1024;
-  // two resident CTAs per SM when three stages fit in half the shared memory
-  int stages = 3, per_sm = 2;
-  if (3 * stage_bytes + fixed > budget / 2) {
-    per_sm = 1;
-    stages = (int)((budget - fixed) / stage_bytes);
-    if (stages > 4) stages = 4;
-  }
-  if (stages < 2) SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "svit_aggregate: N=%d C=%d does not fit shared memory", p.N, p.C);
+  int stages = 3;
+  if (3 * stage_bytes + fixed > budget) stages = 2;
+  if (stages * stage_bytes + fixed > budget)
+    SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "svit_aggregate: N=%d does not fit shared memory", p.N);
   p.stages = stages;
   const size_t smem = stages * stage_bytes + fixed;
+  int per_sm = (int)(budget / (smem + 1024));  // +1 KB per-CTA reservation
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
   auto kern = aggregate_kernel<OutT, BLOCK>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = (int64_t)sm_count() * per_sm;
@@ -233,9 +248,9 @@ int launch(const AggParams& base, cudaStream_t stream) {
 
 template <typename OutT>
 int dispatch_block(const AggParams& p, cudaStream_t stream) {
-  if (p.N <= 16) return launch<OutT, 256>(p, stream);
-  if (p.N <= 32) return launch<OutT, 128>(p, stream);
-  return launch<OutT, 64>(p, stream);
+  if (p.N <= 17) return launch<OutT, 128>(p, stream);  // stage = (N+1) * 4 KB
+  if (p.N <= 35) return launch<OutT, 64>(p, stream);
+  return launch<OutT, 32>(p, stream);
 }
 
 }  // namespace
@@ -248,27 +263,37 @@ extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const f
   SVIT_CHECK_ARG(deltas && ratios && out, "svit_aggregate: null pointer");
   SVIT_CHECK_ARG(P >= 0 && N >= 1 && N <= 64 && C >= 1 && C <= 256, "svit_aggregate: P=%lld N=%d C=%d out of range",
                  (long long)P, N, C);
+  SVIT_CHECK_ARG(out_dtype == SVIT_F32 || out_dtype == SVIT_BF16 || out_dtype == SVIT_F16,
+                 "svit_aggregate: unknown out_dtype %d", out_dtype);
   if (P == 0) return SVIT_OK;
   const int64_t p8 = round_up(P, 8);
   if (!aligned16(deltas) || !aligned16(out) || (w0 && !aligned16(w0)) || delta_stride % 8 || out_stride % 8 ||
       delta_stride < p8 || out_stride < p8)
     SVIT_FAIL(SVIT_ERR_ALIGN,
               "svit_aggregate: pointers must be 16-byte aligned and strides multiples of 8 and >= round_up(P, 8)");
-  AggParams p{};
-  p.deltas = deltas;
-  p.delta_stride = delta_stride;
-  p.w0 = w0;
-  p.ratios = ratios;
-  p.out = out;
-  p.out_stride = out_stride;
-  p.P = P;
-  p.N = N;
-  p.C = C;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (out_dtype) {
-    case SVIT_F32: return dispatch_block<float>(p, s);
-    case SVIT_BF16: return dispatch_block<__nv_bfloat16>(p, s);
-    case SVIT_F16: return dispatch_block<__half>(p, s);
-    default: SVIT_FAIL(SVIT_ERR_ARG, "svit_aggregate: unknown out_dtype %d", out_dtype);
+  const int es = dtype_size(out_dtype);
+  // the ratio rows travel as kernel parameters: at most kMaxRatios floats per launch
+  const int c_per_launch = kMaxRatios / N;
+  for (int c0 = 0; c0 < C; c0 += c_per_launch) {
+    const int cn = C - c0 < c_per_launch ? C - c0 : c_per_launch;
+    AggParams p{};
+    p.deltas = deltas;
+    p.delta_stride = delta_stride;
+    p.w0 = w0;
+    p.out = static_cast<char*>(out) + (size_t)c0 * out_stride * es;
+    p.out_stride = out_stride;
+    p.P = P;
+    p.N = N;
+    p.C = cn;
+    for (int i = 0; i < cn * N; ++i) p.ratios[i] = ratios[(size_t)c0 * N + i];
+    int rc;
+    switch (out_dtype) {
+      case SVIT_F32: rc = dispatch_block<float>(p, s); break;
+      case SVIT_BF16: rc = dispatch_block<__nv_bfloat16>(p, s); break;
+      default: rc = dispatch_block<__half>(p, s); break;
+    }
+    if (rc) return rc;
   }
+  return SVIT_OK;
 }

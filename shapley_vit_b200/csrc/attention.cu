@@ -7,8 +7,11 @@
 // a warp owns one query row at a time: scores (7 keys per lane) -> fp32 softmax in registers ->
 // P V with two output channels per lane.  Scores never touch HBM.
 //
-// This is the fp32 CUDA-core kernel used by every precision mode in round 1; operands may be
-// stored in fp32 / bf16 / fp16, all arithmetic is fp32.
+// This is the fp32 CUDA-core kernel: the exact path for fp32-stored activations (SVIT_PREC_F32 /
+// TF32) and for head sizes other than 64; 16-bit operands with head_dim 64 take the tensor-core
+// kernel in attention_mma.cu.  Operands may be stored in fp32 / bf16 / fp16, all arithmetic is fp32.
+#include <cstdlib>
+
 #include "elementwise.h"
 
 namespace svit {
@@ -124,6 +127,13 @@ int attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, int 
               cudaStream_t stream) {
   if (n_seq == 0) return SVIT_OK;
   SVIT_CHECK_ARG(Tn >= 1 && Tn <= 256, "attention: T=%d out of range (1..256)", Tn);
+  // 16-bit operands with the ViT head size go to the tensor-core kernel (attention_mma.cu)
+  static const bool force_simt = [] {
+    const char* e = getenv("SVIT_ATTENTION_SIMT");
+    return e && e[0] == '1';
+  }();
+  if (!force_simt && head_dim == 64 && (dtype == SVIT_F16 || dtype == SVIT_BF16) && (heads * head_dim) % 8 == 0)
+    return attention_mma(qkv, ctx, dtype, n_seq, Tn, heads, stream);
   switch (dtype) {
     case SVIT_F32: return dispatch_d<float>(qkv, ctx, n_seq, Tn, heads, head_dim, stream);
     case SVIT_BF16: return dispatch_d<__nv_bfloat16>(qkv, ctx, n_seq, Tn, heads, head_dim, stream);

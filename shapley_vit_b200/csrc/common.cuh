@@ -60,12 +60,28 @@ template <> struct Cvt<__nv_bfloat16> {
 };
 template <> struct Cvt<__half> {
   static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
-  // saturating: a finite fp32 value never becomes inf in the operand type
+  // saturating (cvt.rn.satfinite): a finite fp32 value never becomes inf in the operand type
   static __device__ __forceinline__ __half from_f(float v) {
-    v = fminf(fmaxf(v, -65504.f), 65504.f);
-    return __float2half_rn(v);
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return __ushort_as_half(r);
   }
 };
+
+// two floats -> packed fp16x2 / bf16x2 (lo in the low half), one F2FP instruction
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float lo, float hi) { return pack_f16x2_sat(lo, hi); }
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float lo, float hi) { return pack_bf16x2(lo, hi); }
 
 // 4 consecutive elements, one vector store (p must be aligned to 4 elements)
 template <typename T>
@@ -76,20 +92,11 @@ __device__ __forceinline__ void store4<float>(float* p, float a, float b, float 
 }
 template <>
 __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&lo);
-  u.y = *reinterpret_cast<uint32_t*>(&hi);
-  *reinterpret_cast<uint2*>(p) = u;
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
 }
 template <>
 __device__ __forceinline__ void store4<__half>(__half* p, float a, float b, float c, float d) {
-  __half2 lo = __halves2half2(Cvt<__half>::from_f(a), Cvt<__half>::from_f(b));
-  __half2 hi = __halves2half2(Cvt<__half>::from_f(c), Cvt<__half>::from_f(d));
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&lo);
-  u.y = *reinterpret_cast<uint32_t*>(&hi);
-  *reinterpret_cast<uint2*>(p) = u;
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_f16x2_sat(a, b), pack_f16x2_sat(c, d));
 }
 
 // exact-erf GELU, the HF "gelu" activation (torch.nn.functional.gelu, approximate='none')

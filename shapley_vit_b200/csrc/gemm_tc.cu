@@ -168,27 +168,15 @@ __device__ __forceinline__ void epilogue_row32(const EpiArgs& e, int g, int r, i
     } else if (e.out_dtype == SVIT_BF16) {
       uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + idx);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&p0), u.y = *reinterpret_cast<uint32_t*>(&p1);
-        u.z = *reinterpret_cast<uint32_t*>(&p2), u.w = *reinterpret_cast<uint32_t*>(&p3);
-        o[i] = u;
-      }
+      for (int i = 0; i < 4; ++i)
+        o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                          pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
     } else {
       uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + idx);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __half2 p0 = __halves2half2(Cvt<__half>::from_f(v[8 * i]), Cvt<__half>::from_f(v[8 * i + 1]));
-        __half2 p1 = __halves2half2(Cvt<__half>::from_f(v[8 * i + 2]), Cvt<__half>::from_f(v[8 * i + 3]));
-        __half2 p2 = __halves2half2(Cvt<__half>::from_f(v[8 * i + 4]), Cvt<__half>::from_f(v[8 * i + 5]));
-        __half2 p3 = __halves2half2(Cvt<__half>::from_f(v[8 * i + 6]), Cvt<__half>::from_f(v[8 * i + 7]));
-        uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&p0), u.y = *reinterpret_cast<uint32_t*>(&p1);
-        u.z = *reinterpret_cast<uint32_t*>(&p2), u.w = *reinterpret_cast<uint32_t*>(&p3);
-        o[i] = u;
-      }
+      for (int i = 0; i < 4; ++i)
+        o[i] = make_uint4(pack_f16x2_sat(v[8 * i], v[8 * i + 1]), pack_f16x2_sat(v[8 * i + 2], v[8 * i + 3]),
+                          pack_f16x2_sat(v[8 * i + 4], v[8 * i + 5]), pack_f16x2_sat(v[8 * i + 6], v[8 * i + 7]));
     }
   } else {  // ragged N: element-wise (static indices keep v[] in registers)
 #pragma unroll

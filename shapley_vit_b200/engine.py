@@ -6,7 +6,7 @@ fed_client_contribution/game.py:88-107): build FedAvg ratios, aggregate the memb
 add W0, ``load_state_dict``, then run ``evaluation`` over the whole validation loader with
 an H2D copy per batch and two host syncs per batch.  Here, per BATCH of coalitions:
 
-    ratios [C, N] (host, fp64 -> fp32)  --H2D-->
+    ratios [C, N] (host, fp64 -> fp32)  --kernel parameters-->
     svit_aggregate (vec region, fp32)  +  svit_aggregate (mat region, operand dtype)
     for each chunk of validation images:  svit_forward_batched -> logits [C, n_val, n_cls]
     svit_score -> correct [C] int64, loss_sum [C] fp64   --D2H-->
@@ -127,12 +127,6 @@ class CoalitionEngine:
             self.wvec = torch.empty((cb, self.lay.vec_size), dtype=torch.float32, device=self.device)
             self.wmat = torch.empty((cb, self.lay.mat_size), dtype=self.plan.operand_dtype, device=self.device)
             self.logits = torch.empty((cb, self.n_val, cfg.n_cls), dtype=torch.float32, device=self.device)
-            # ring of pinned staging rows for the per-batch ratio upload (reused only after the
-            # copy that read them has completed)
-            self._ring = [(torch.zeros((cb, self.n_clients), dtype=torch.float32, pin_memory=True),
-                           torch.zeros((cb, self.n_clients), dtype=torch.float32, device=self.device),
-                           torch.cuda.Event()) for _ in range(4)]
-            self._ring_pos = 0
             torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ #
@@ -152,14 +146,9 @@ class CoalitionEngine:
         """One batch of <= coalition_batch coalitions given their dense ratio rows."""
         Cn = len(ratio_rows)
         lay, cfg = self.lay, self.cfg
-        rh, rd, ev = self._ring[self._ring_pos]
-        self._ring_pos = (self._ring_pos + 1) % len(self._ring)
-        ev.synchronize()
-        rh.zero_()
-        rh[:Cn] = torch.as_tensor(ratio_rows, dtype=torch.float64).to(torch.float32)
-        rd.copy_(rh, non_blocking=True)
-        ev.record()
-        ratios = rd[:Cn]
+        # FedAvg ratios: fp64 on the host (as the reference computes them), rounded once to fp32;
+        # svit_aggregate copies them into its kernel parameters (no separate H2D copy)
+        ratios = torch.as_tensor(ratio_rows, dtype=torch.float64).to(torch.float32)
         V, Mz = lay.vec_size, lay.mat_size
         w0v = self.w0[:V] if self.w0 is not None else None
         w0m = self.w0[V:] if self.w0 is not None else None
@@ -208,7 +197,7 @@ class CoalitionEngine:
         """Score one explicit model (the reference's plain ``evaluation(args, net, loader)``)."""
         with torch.cuda.device(self.device):
             row = pack_state_dict(self.lay, sd).to(self.device).unsqueeze(0)
-            one = torch.ones((1, 1), dtype=torch.float32, device=self.device)
+            one = torch.ones((1, 1), dtype=torch.float32)
             V = self.lay.vec_size
             ops.aggregate(row[:, :V], None, one, out=self.wvec[:1], P=V)
             ops.aggregate(row[:, V:], None, one, out=self.wmat[:1], P=self.lay.mat_size)
@@ -226,5 +215,5 @@ class CoalitionEngine:
     def aggregated_rows(self, ratio_rows: Sequence[Sequence[float]], dtype=torch.float32) -> torch.Tensor:
         """Aggregated models (plan layout, [C, total]) for parity checks of K1."""
         with torch.cuda.device(self.device):
-            r = torch.as_tensor(ratio_rows, dtype=torch.float64).to(torch.float32).to(self.device)
+            r = torch.as_tensor(ratio_rows, dtype=torch.float64).to(torch.float32)
             return ops.aggregate(self.deltas, self.w0, r, out_dtype=dtype)

@@ -70,7 +70,7 @@ def get_aggregated_model(nets: Sequence[Dict[str, torch.Tensor]], ratio: Sequenc
     stride = (P + 7) // 8 * 8
     stacked = torch.zeros((len(nets), stride), dtype=torch.float32, device=dev)
     stacked[:, :P] = flat.to(dev)
-    r = torch.tensor([list(ratio)], dtype=torch.float64).to(torch.float32).to(dev)
+    r = torch.tensor([list(ratio)], dtype=torch.float64).to(torch.float32)
     out = ops.aggregate(stacked, None, r, P=P)[0, :P]
     res: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     o = 0

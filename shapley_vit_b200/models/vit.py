@@ -74,7 +74,7 @@ class ViTForImageClassification(nn.Module):
             self._plan = ops.Plan(self.cfg, PRECISIONS[self.precision], 1, max(B, 1), dev)
         plan = self._plan
         row = pack_state_dict(lay, {k: v.detach() for k, v in self.state_dict().items()}).to(dev).unsqueeze(0)
-        one = torch.ones((1, 1), dtype=torch.float32, device=dev)
+        one = torch.ones((1, 1), dtype=torch.float32)
         V = lay.vec_size
         wvec = ops.aggregate(row[:, :V], None, one, out_dtype=torch.float32, P=V)
         wmat = ops.aggregate(row[:, V:], None, one, out_dtype=plan.operand_dtype, P=lay.mat_size)

@@ -35,9 +35,10 @@ def aggregate(deltas: torch.Tensor, w0: Optional[torch.Tensor], ratios: torch.Te
               out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None,
               P: Optional[int] = None) -> torch.Tensor:
     """K1.  deltas [N, stride] fp32 (row-contiguous), w0 [>=P] fp32 or None, ratios [C, N] fp32
-    (0 = non-member).  Returns out [C, out_stride] with out[c, :P] = w0 + sum_j ratios[c, j] * deltas[j]."""
+    on the HOST (0 = non-member; a CUDA tensor is copied back, which synchronises).
+    Returns out [C, out_stride] with out[c, :P] = w0 + sum_j ratios[c, j] * deltas[j]."""
     _cuda(deltas, "deltas", torch.float32)
-    _cuda(ratios, "ratios", torch.float32)
+    ratios = ratios.detach().to("cpu", torch.float32)
     if deltas.dim() != 2 or deltas.stride(1) != 1:
         raise ValueError("deltas must be [N, P] with unit inner stride")
     N, width = deltas.shape

@@ -144,7 +144,8 @@ def test_patchify(ops, image):
     assert torch.equal(got, want)
 
 
-@pytest.mark.parametrize("T,heads,d", [(5, 3, 64), (197, 12, 64), (197, 2, 32), (50, 2, 128)])
+@pytest.mark.parametrize("T,heads,d", [(5, 3, 64), (197, 12, 64), (197, 2, 32), (50, 2, 128), (16, 2, 64), (17, 1, 64),
+                                       (64, 3, 64), (208, 2, 64), (209, 1, 64), (256, 1, 64)])
 def test_attention_fp32(ops, T, heads, d):
     n_seq, h = 3, heads * d
     qkv = gen(n_seq, T, 3 * h, seed=T)
@@ -152,8 +153,12 @@ def test_attention_fp32(ops, T, heads, d):
     want = (torch.softmax(q @ k.transpose(2, 3) * d ** -0.5, dim=-1) @ v).transpose(1, 2).reshape(n_seq, T, h)
     got = ops.attention(qkv.cuda(), heads).cpu()
     assert (got - want).abs().max() < 2e-5
-    got16 = ops.attention(qkv.half().cuda(), heads).cpu().float()
-    assert (got16 - want).abs().max() < 5e-3
+    for dt, tol in ((torch.float16, 5e-3), (torch.bfloat16, 3e-2)):     # d == 64: tensor-core kernel
+        q16 = qkv.to(dt)
+        q, k, v = (t_.float().view(n_seq, T, heads, d).transpose(1, 2) for t_ in q16.split(h, dim=2))
+        want16 = (torch.softmax(q @ k.transpose(2, 3) * d ** -0.5, dim=-1) @ v).transpose(1, 2).reshape(n_seq, T, h)
+        got16 = ops.attention(q16.cuda(), heads).cpu().float()
+        assert (got16 - want16).abs().max() < tol
 
 
 # ----------------------------------------------------------------------------- GEMM
@@ -207,7 +212,7 @@ def test_gemm_tcgen05_matches_cuda_core_gemm(ops, prec_name, G, M, N, K, monkeyp
     got = ops.gemm(prec, A.cuda(), B.cuda(), bias=bias.cuda(), residual=res.cuda(), out_dtype=torch.float32).cpu()
     if prec_name == "tf32":   # the tensor core truncates fp32 operands to 10 mantissa bits
         want = ref_gemm(A, B, bias, res)
-        tol = 2e-3 * (K / 64) ** 0.5
+        tol = 4e-3 * (K / 64) ** 0.5
     else:
         want = ref_gemm(A.float(), B.float(), bias, res)
         tol = 1e-4 * (K / 64) ** 0.5
