@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Summarise ncu artefacts brought back in gpurun_out/ into small text files under profiles/.
+
+    python scripts/ncu_summary.py launches gpurun_out/r01_launches.csv  > profiles/r01_launches.md
+    python scripts/ncu_summary.py full gpurun_out/r01_gemm.ncu-rep      > profiles/r01_gemm.md
+"""
+import csv
+import io
+import subprocess
+import sys
+from collections import defaultdict
+
+KEYS = [
+    "gpu__time_duration.sum", "sm__cycles_elapsed.max", "launch__grid_size", "launch__block_size",
+    "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard_per_warp_active.pct",
+]
+
+
+def launches(path):
+    rows = list(csv.reader(open(path)))
+    h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    hdr = rows[h]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    tot, cnt = defaultdict(float), defaultdict(int)
+    for r in rows[h + 1:]:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", ""))
+        scale = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r[ui], 1e-6)
+        name = r[ki].split("(")[0].replace("void ", "").replace("svit::<unnamed>::", "")
+        tot[name] += v * scale
+        cnt[name] += 1
+    total = sum(tot.values())
+    print(f"# ncu launch list: {path}\n")
+    print("per-launch times are cold-cache and serialised under ncu: compare SHARES, not absolutes\n")
+    print("| kernel | launches | total ms | avg us | share |\n|---|---:|---:|---:|---:|")
+    for n in sorted(tot, key=tot.get, reverse=True):
+        print(f"| `{n}` | {cnt[n]} | {tot[n]:.3f} | {1e3 * tot[n] / cnt[n]:.1f} | {100 * tot[n] / total:.1f}% |")
+    print(f"| total | {sum(cnt.values())} | {total:.3f} | | |")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    print(f"# ncu --set full: {path}\n")
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        print(f"## `{name[:110]}`\n\n| metric | unit | value |\n|---|---|---:|")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"| {k} | {units[i]} | {r[i]} |")
+        print()
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])

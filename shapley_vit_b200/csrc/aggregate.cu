@@ -94,6 +94,8 @@ struct AggParams {
   // FedAvg ratios [C, N], by value: they reach the SM through the constant bank, so the
   // membership test (ratio != 0) and the multiplier are warp-uniform operands, not loads.
   float ratios[kMaxRatios];
+  // membership bit masks: masks[(c0 / kCChunk) * N + j] bit cc <=> ratios[(c0 + cc) * N + j] != 0
+  uint32_t masks[kMaxRatios / kCChunk];
 };
 
 // dynamic smem: [STAGES][(N+1)][TILE] floats | mbarriers [STAGES]
@@ -175,14 +177,20 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
           const float4 da = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + ea);
           const float4 db = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + eb);
           const float d[kVec] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+          // One mask word decides all 8 memberships; the 8 ratios are fetched unconditionally
+          // (constant bank, warp-uniform) so no load sits on a branch's critical path.
+          const uint32_t m = p.masks[(c0 / kCChunk) * N + j];
+          float r[kCChunk];
 #pragma unroll
           for (int cc = 0; cc < kCChunk; ++cc) {
-            if (c0 + cc < C) {
-              const float r = p.ratios[(c0 + cc) * N + j];  // constant bank, warp-uniform
-              if (r != 0.f) {
+            r[cc] = p.ratios[(c0 + cc) * N + j];
+            asm volatile("" : "+f"(r[cc]));
+          }
 #pragma unroll
-                for (int q = 0; q < kVec; ++q) acc[cc][q] = __fadd_rn(acc[cc][q], __fmul_rn(r, d[q]));
-              }
+          for (int cc = 0; cc < kCChunk; ++cc) {
+            if (m & (1u << cc)) {
+#pragma unroll
+              for (int q = 0; q < kVec; ++q) acc[cc][q] = __fadd_rn(acc[cc][q], __fmul_rn(r[cc], d[q]));
             }
           }
         }
@@ -274,7 +282,7 @@ extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const f
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int es = dtype_size(out_dtype);
   // the ratio rows travel as kernel parameters: at most kMaxRatios floats per launch
-  const int c_per_launch = kMaxRatios / N;
+  const int c_per_launch = (kMaxRatios / N) / kCChunk * kCChunk;
   for (int c0 = 0; c0 < C; c0 += c_per_launch) {
     const int cn = C - c0 < c_per_launch ? C - c0 : c_per_launch;
     AggParams p{};
@@ -286,7 +294,11 @@ extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const f
     p.P = P;
     p.N = N;
     p.C = cn;
+    // (p is value-initialised: ratios of the padding coalitions up to a multiple of 8 are 0)
     for (int i = 0; i < cn * N; ++i) p.ratios[i] = ratios[(size_t)c0 * N + i];
+    for (int c = 0; c < cn; ++c)
+      for (int j = 0; j < N; ++j)
+        if (p.ratios[c * N + j] != 0.f) p.masks[(c / kCChunk) * N + j] |= 1u << (c % kCChunk);
     int rc;
     switch (out_dtype) {
       case SVIT_F32: rc = dispatch_block<float>(p, s); break;
