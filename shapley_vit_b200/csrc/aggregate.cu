@@ -10,9 +10,10 @@
 // A persistent CTA owns tiles of TILE consecutive parameters; one elected thread stages the
 // N+1 rows of a tile into shared memory with 1-D TMA bulk copies (cp.async.bulk, completion on
 // an mbarrier), STAGES tiles deep, so the loads in flight do not depend on occupancy or
-// registers.  Each thread owns 4 consecutive parameters, keeps 16 coalition accumulators
-// (x4 lanes) in registers, walks the clients in ascending order reading its float4 from shared
-// memory, and writes every coalition's row with 64/128-bit streaming stores.
+// registers.  Each thread owns 2 x 4 consecutive parameters, keeps 8 coalition accumulators
+// (x8 lanes) in registers, walks the clients in ascending order reading its float4 from shared
+// memory, and writes every coalition's row with 64/128-bit streaming stores.  The arithmetic is
+// FMUL2 (packed fp32x2 products) + FADD: three issue slots per two parameters, same rounding.
 //
 // Arithmetic: every product and every sum is a separately rounded fp32 operation
 // (__fmul_rn/__fadd_rn; ptxas would otherwise contract to FMA), in ascending client order,
@@ -64,21 +65,36 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
+// r * d for two parameters in one issue slot (sm_100 FMUL2, IEEE round-to-nearest like FMUL).
+// The sums stay scalar FADDs on purpose: ptxas 12.9 contracts a packed product feeding a packed
+// sum into one FFMA2 even when both carry .rn (it does not for scalar code), and a fused
+// multiply-add rounds once where the reference (`ratio * delta`, then `agg + ...`, on fp32
+// tensors) rounds twice.
+__device__ __forceinline__ float2 mul2(float r, float2 d) {
+  float2 o;
+  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(o.x), "=f"(o.y)
+      : "f"(r), "f"(d.x), "f"(d.y));
+  return o;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+
 // 4 consecutive outputs, one streaming vector store (8 bytes for fp16/bf16, 16 for fp32)
 template <typename OutT> struct Store4;
 template <> struct Store4<float> {
-  static __device__ __forceinline__ void st(float* p, const float* v) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  static __device__ __forceinline__ void st(float* p, float2 a, float2 b) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(a.x, a.y, b.x, b.y));
   }
 };
 template <> struct Store4<__nv_bfloat16> {
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* v) {
-    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3])));
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float2 a, float2 b) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y)));
   }
 };
 template <> struct Store4<__half> {
-  static __device__ __forceinline__ void st(__half* p, const float* v) {
-    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_f16x2_sat(v[0], v[1]), pack_f16x2_sat(v[2], v[3])));
+  static __device__ __forceinline__ void st(__half* p, float2 a, float2 b) {
+    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_f16x2_sat(a.x, a.y), pack_f16x2_sat(b.x, b.y)));
   }
 };
 
@@ -91,28 +107,34 @@ struct AggParams {
   int64_t P;
   int N, C, stages;
   int64_t num_tiles;
-  // FedAvg ratios [C, N], by value: they reach the SM through the constant bank, so the
-  // membership test (ratio != 0) and the multiplier are warp-uniform operands, not loads.
+  // FedAvg ratios, by value, in [chunk of 8 coalitions][client j][8] order (0 = not a member or
+  // padding), and one membership word per (chunk, j): bit cc <=> coalition 8*chunk+cc contains j.
+  // Each CTA copies both tables to shared memory once; the inner loop then reads 8 ratios and
+  // the mask with three broadcast loads.
   float ratios[kMaxRatios];
-  // membership bit masks: masks[(c0 / kCChunk) * N + j] bit cc <=> ratios[(c0 + cc) * N + j] != 0
   uint32_t masks[kMaxRatios / kCChunk];
 };
 
-// dynamic smem: [STAGES][(N+1)][TILE] floats | mbarriers [STAGES]
+// dynamic smem: [STAGES][(N+1)][TILE] floats | ratio table | mask table | mbarriers [STAGES]
 template <typename OutT, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant__ AggParams p) {
   constexpr int TILE = BLOCK * kVec;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.N, C = p.C, S = p.stages;
   const int rows = N + 1;  // row N holds W_0
+  const int nchunks = (C + kCChunk - 1) / kCChunk;
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)S * rows * TILE);
+  float* s_ratio = stage_base + (size_t)S * rows * TILE;
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_ratio + (size_t)nchunks * N * kCChunk);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + ((nchunks * N + 1) & ~1));
   const int tid = threadIdx.x;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < nchunks * N * kCChunk; i += BLOCK) s_ratio[i] = p.ratios[i];
+  for (int i = tid; i < nchunks * N; i += BLOCK) s_mask[i] = p.masks[i];
   __syncthreads();
 
   const int64_t P = p.P;
@@ -154,62 +176,60 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
     // 128-bit shared-memory read of a warp is contiguous (conflict-free).
     const int ea = tid * 4, eb = TILE / 2 + tid * 4;
     if (ea < len) {
-      const bool has_b = eb < len;
-      float w[kVec];
+      float2 w[4];
 #pragma unroll
-      for (int q = 0; q < kVec; ++q) w[q] = 0.f;
+      for (int q = 0; q < 4; ++q) w[q] = make_float2(0.f, 0.f);
       if (p.w0) {
         const float4 a = *reinterpret_cast<const float4*>(st + (size_t)N * TILE + ea);
-        w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w;
-        if (has_b) {
-          const float4 b = *reinterpret_cast<const float4*>(st + (size_t)N * TILE + eb);
-          w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
-        }
+        const float4 b = *reinterpret_cast<const float4*>(st + (size_t)N * TILE + eb);
+        w[0] = make_float2(a.x, a.y), w[1] = make_float2(a.z, a.w);
+        w[2] = make_float2(b.x, b.y), w[3] = make_float2(b.z, b.w);
       }
       OutT* outp = reinterpret_cast<OutT*>(p.out) + t * TILE;
-      for (int c0 = 0; c0 < C; c0 += kCChunk) {
-        float acc[kCChunk][kVec];
+#pragma unroll 1
+      for (int ch = 0; ch < nchunks; ++ch) {
+        float2 acc[kCChunk][4];
 #pragma unroll
         for (int cc = 0; cc < kCChunk; ++cc)
 #pragma unroll
-          for (int q = 0; q < kVec; ++q) acc[cc][q] = 0.f;
+          for (int q = 0; q < 4; ++q) acc[cc][q] = make_float2(0.f, 0.f);
+        const float4* rt = reinterpret_cast<const float4*>(s_ratio + (size_t)ch * N * kCChunk);
+        const uint32_t* mk = s_mask + ch * N;
+#pragma unroll 1
         for (int j = 0; j < N; ++j) {
           const float4 da = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + ea);
           const float4 db = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + eb);
-          const float d[kVec] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-          // One mask word decides all 8 memberships; the 8 ratios are fetched unconditionally
-          // (constant bank, warp-uniform) so no load sits on a branch's critical path.
-          const uint32_t m = p.masks[(c0 / kCChunk) * N + j];
-          float r[kCChunk];
+          const float2 d[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y),
+                               make_float2(db.z, db.w)};
+          const uint32_t m = mk[j];
+          const float4 r0 = rt[2 * j], r1 = rt[2 * j + 1];
+          const float r[kCChunk] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
           for (int cc = 0; cc < kCChunk; ++cc) {
-            r[cc] = p.ratios[(c0 + cc) * N + j];
-            asm volatile("" : "+f"(r[cc]));
-          }
+            if (m & (1u << cc)) {  // warp-uniform: a real branch skips the 8 packed operations
 #pragma unroll
-          for (int cc = 0; cc < kCChunk; ++cc) {
-            if (m & (1u << cc)) {
-#pragma unroll
-              for (int q = 0; q < kVec; ++q) acc[cc][q] = __fadd_rn(acc[cc][q], __fmul_rn(r[cc], d[q]));
+              for (int q = 0; q < 4; ++q) acc[cc][q] = add2(acc[cc][q], mul2(r[cc], d[q]));
             }
           }
         }
 #pragma unroll
         for (int cc = 0; cc < kCChunk; ++cc) {
-          if (c0 + cc < C) {
-            float v[kVec];
+          const int c = ch * kCChunk + cc;
+          if (c < C) {
+            float2 v[4];
 #pragma unroll
-            for (int q = 0; q < kVec; ++q) v[q] = __fadd_rn(w[q], acc[cc][q]);
-            OutT* o = outp + (size_t)(c0 + cc) * p.out_stride;
+            for (int q = 0; q < 4; ++q) v[q] = add2(w[q], acc[cc][q]);
+            OutT* o = outp + (size_t)c * p.out_stride;
 #pragma unroll
             for (int grp = 0; grp < 2; ++grp) {
               const int e = grp ? eb : ea;
               if (e + 4 <= len) {
-                Store4<OutT>::st(o + e, v + 4 * grp);
+                Store4<OutT>::st(o + e, v[2 * grp], v[2 * grp + 1]);
               } else {  // ragged tail: element-wise
+                const float f[4] = {v[2 * grp].x, v[2 * grp].y, v[2 * grp + 1].x, v[2 * grp + 1].y};
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                  if (e + q < len) o[e + q] = Cvt<OutT>::from_f(v[4 * grp + q]);
+                  if (e + q < len) o[e + q] = Cvt<OutT>::from_f(f[q]);
               }
             }
           }
@@ -233,18 +253,22 @@ int launch(const AggParams& base, cudaStream_t stream) {
   AggParams p = base;
   constexpr int TILE = BLOCK * kVec;
   p.num_tiles = (p.P + TILE - 1) / TILE;
+  const int nchunks = (p.C + kCChunk - 1) / kCChunk;
   const size_t stage_bytes = (size_t)(p.N + 1) * TILE * 4;
-  const size_t fixed = 8 * 8;
+  const size_t fixed = (size_t)nchunks * p.N * kCChunk * 4 + (size_t)((nchunks * p.N + 1) & ~1) * 4 + 8 * 8;
   const size_t budget = 227 * 1024;
-  int stages = 3;
-  if (3 * stage_bytes + fixed > budget) stages = 2;
+  // Two stages per CTA and as many CTAs per SM as fit: the loads in flight per SM are the same as
+  // with deeper rings, but more warps hide the shared-memory and branch latency of the inner loop.
+  int stages = 2;
   if (stages * stage_bytes + fixed > budget)
     SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "svit_aggregate: N=%d does not fit shared memory", p.N);
+  if (4 * stage_bytes + fixed + 1024 <= budget / 3) stages = 4;
+  else if (3 * stage_bytes + fixed + 1024 <= budget / 3) stages = 3;
   p.stages = stages;
   const size_t smem = stages * stage_bytes + fixed;
   int per_sm = (int)(budget / (smem + 1024));  // +1 KB per-CTA reservation
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  if (per_sm > 8) per_sm = 8;
   auto kern = aggregate_kernel<OutT, BLOCK>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = (int64_t)sm_count() * per_sm;
@@ -294,11 +318,13 @@ extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const f
     p.P = P;
     p.N = N;
     p.C = cn;
-    // (p is value-initialised: ratios of the padding coalitions up to a multiple of 8 are 0)
-    for (int i = 0; i < cn * N; ++i) p.ratios[i] = ratios[(size_t)c0 * N + i];
+    // p is value-initialised: ratios of the padding coalitions up to a multiple of 8 stay 0
     for (int c = 0; c < cn; ++c)
-      for (int j = 0; j < N; ++j)
-        if (p.ratios[c * N + j] != 0.f) p.masks[(c / kCChunk) * N + j] |= 1u << (c % kCChunk);
+      for (int j = 0; j < N; ++j) {
+        const float r = ratios[(size_t)(c0 + c) * N + j];
+        p.ratios[((size_t)(c / kCChunk) * N + j) * kCChunk + c % kCChunk] = r;
+        if (r != 0.f) p.masks[(c / kCChunk) * N + j] |= 1u << (c % kCChunk);
+      }
     int rc;
     switch (out_dtype) {
       case SVIT_F32: rc = dispatch_block<float>(p, s); break;

@@ -17,7 +17,20 @@
 //                              tile i overlaps the MMAs of tile i+1.
 // Tile order: n fastest, then m, then group, so CTAs running concurrently share A rows in L2.
 // Operand precisions: bf16 / fp16 (kind::f16, K=16 per MMA) and tf32 (kind::tf32, K=8).
+//
+// Two kernels share the roles above:
+//   gemm_tc_kernel   one CTA per 128 x BN tile (cta_group::1); any N (BN = 128 | 256)
+//   gemm_tc2_kernel  a CTA PAIR (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile: each CTA
+//                    stages its own 128 rows of A and HALF of the B tile, the leader's MMA thread
+//                    issues 256 x 256 x 16 instructions that read both CTAs' shared memory and
+//                    write both CTAs' TMEM.  Per CTA and k-block that is 32 KB of L2 -> SM traffic
+//                    instead of 48 KB for the same 128 x 256 outputs: with K = 768 the 1-CTA kernel
+//                    is bound by L2 -> SM bandwidth (96 B/clk/SM wanted), not by the tensor pipe.
+//                    Used whenever N % 256 == 0 and M >= 256.
 #include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
 
 #include "epilogue.cuh"
 
@@ -27,16 +40,19 @@ namespace {
 constexpr int BM = 128;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kStagingPerWarp = 32 * 128;  // one 32-row x 32-column fp32 chunk per epilogue warp
+constexpr int kBiasPerWarp = 128 * 4;      // the bias slice of the warp's 128 (BN = 256) columns of a tile
 
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = BN == 256 ? 3 : 5;  // (1-CTA kernel: small / ragged-N problems only)
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + NUM_BARS * 8 + 16 + 1024;
+  static constexpr int STAGING_BYTES = kEpiWarps * (kStagingPerWarp + kBiasPerWarp);
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + NUM_BARS * 8 + 16 + 1024;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -83,6 +99,70 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// One lane of a converged warp (the lowest): the loops of the producer and MMA warps stay
+// warp-uniform, so their counters and addresses live in uniform registers and the issuing lane
+// executes ~10 instead of ~20 SASS instructions per tcgen05.mma (the single-thread form made the
+// ISSUE loop, not the tensor pipe, the pacer: 71 % tensor-active in profiles/r02_gemm_plain).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// ---- cluster / CTA-pair helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` (a shared::cta address) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // relaxed: the TMEM reads it publishes are ordered by tcgen05.wait::ld + fence::before_thread_sync;
+  // a release at cluster scope would first drain every global store of the epilogue (MEMBAR.GPU)
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; the completion bytes are counted on the barrier at
+// shared::cluster address `bar_cluster` (the LEADER's full barrier)
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1,
+                                                 int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrive (once the MMAs issued so far complete) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if constexpr (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
 template <int KIND>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   if constexpr (KIND == 0) {
@@ -100,7 +180,7 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
   }
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (row) i
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -112,88 +192,291 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// the same descriptor `bytes` further into shared memory (start-address field is in 16-byte units)
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t bytes) { return desc + (bytes >> 4); }
 
 struct TcShape {
   int G, M, N, K;
   int tiles_m, tiles_n, num_kb;
   int64_t total_tiles;
   int a_grouped;  // 0: A shared by all groups
+  int flags;      // tuning experiments (SVIT_GEMM_FLAGS)
 };
 
-// ---- epilogue for 32 consecutive columns of one output row ---------------------------------
-__device__ __forceinline__ void epilogue_row32(const EpiArgs& e, int g, int r, int n, float* v) {
-  const int64_t orow = epi_out_row(e, r);
-  const int N = e.N;
-  if (n + 32 <= N && (N & 7) == 0) {
-    if (e.bias) {
-      const float4* b = reinterpret_cast<const float4*>(e.bias + (size_t)g * e.bias_gs + n);
+// ---- packed fp32x2 arithmetic (FFMA2: two IEEE fp32 FMAs per issue slot on sm_100) ------------
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Exact (erf) GELU of two values without erff():  gelu(x) = x * Phi(x),  Phi(-a) = 2^E(-a) for
+// a = |x| with E a degree-7 fit of log2(erfc(a / sqrt 2) / 2) on [0, 6] (E -> -inf beyond), so
+//   gelu(x) = max(x, 0) - a * 2^E(-a)
+// for either sign.  |error| <= 4.8e-7 absolute (the fp32 rounding of the result), <= 8e-6 relative
+// for |x| < 3: two decimal orders below the rounding of the 16-bit / tf32 operand it feeds.
+// 7 + 1 FFMA2, 2 MUFU.EX2, 2 FMNMX per pair -- erff() costs ~4x the issue slots, which made the
+// MLP-up epilogue, not the tensor pipe, the bound of that GEMM.
+__device__ __forceinline__ void gelu_pair(float& x0, float& x1) {
+  const float2 ma = make_float2(-fabsf(x0), -fabsf(x1));
+  float2 p = make_float2(7.487684570e-07f, 7.487684570e-07f);
+  p = ffma2(p, ma, make_float2(4.349770097e-05f, 4.349770097e-05f));
+  p = ffma2(p, ma, make_float2(8.161957958e-04f, 8.161957958e-04f));
+  p = ffma2(p, ma, make_float2(8.163100109e-03f, 8.163100109e-03f));
+  p = ffma2(p, ma, make_float2(5.344700068e-02f, 5.344700068e-02f));
+  p = ffma2(p, ma, make_float2(-4.588129818e-01f, -4.588129818e-01f));
+  p = ffma2(p, ma, make_float2(1.151166201e+00f, 1.151166201e+00f));
+  p = ffma2(p, ma, make_float2(-9.999985099e-01f, -9.999985099e-01f));
+  const float2 e = make_float2(ex2_approx(p.x), ex2_approx(p.y));
+  const float2 r = ffma2(ma, e, make_float2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+  x0 = r.x, x1 = r.y;
+}
+
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+
+// ---- epilogue of one 32-row x 32-column accumulator chunk ------------------------------------
+// tcgen05.ld hands every thread one ROW (32 consecutive columns).  Storing that layout directly
+// makes each warp store touch 32 different cache lines (the LSU, not the tensor pipe, then paces
+// the GEMM).  So: bias + GELU in the row layout, transpose through a per-warp swizzled shared
+// memory tile (conflict-free both ways), then position-embedding / residual adds and the global
+// stores in a COALESCED layout (a quarter-warp covers one contiguous 128-byte row segment).
+
+enum { EPI_DIRECT = 0, EPI_RESIDUAL = 1, EPI_GENERIC = 2 };  // see epilogue_chunk
+
+// the residual fragment of one chunk in the coalesced layout (8 x float4 per lane), read ahead of use
+template <int MODE>
+__device__ __forceinline__ void residual_prefetch(const EpiArgs& e, int g, int m_slab, int n, int lane, float4 (&res)[8]) {
+  const int jj = lane & 7, rsub = lane >> 3;
+  const float* base = e.residual + (size_t)g * e.residual_gs + n + jj * 4;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 t = __ldg(b + i);
-        v[4 * i] += t.x, v[4 * i + 1] += t.y, v[4 * i + 2] += t.z, v[4 * i + 3] += t.w;
-      }
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_slab + i * 4 + rsub;
+    res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < e.M) {
+      const int64_t orow = MODE == EPI_GENERIC ? epi_out_row(e, row) : (int64_t)row;
+      res[i] = *reinterpret_cast<const float4*>(base + (size_t)orow * e.N);
     }
-    if (e.gelu) {
+  }
+}
+
+// Epilogue modes: the kernels are compiled once per mode so that the hot loop of an epilogue warp
+// holds only the code it runs (a single generic body overflowed the instruction cache: the
+// epilogue warps stalled on instruction fetch, profiles/r05_gemm_proj).
+//   EPI_DIRECT    + bias (+ GELU) -> cast -> store; no row remap           (QKV, MLP-up)
+//   EPI_RESIDUAL  + bias -> + fp32 residual -> fp32 store; no row remap    (attention out-proj, MLP-down)
+//   EPI_GENERIC   everything decided at run time                           (patch embedding, odd callers)
+
+//   v        the thread's 32 accumulators (row m_slab + lane, columns n .. n+31)
+//   stg      this warp's staging tile (kStagingPerWarp bytes of shared memory)
+//   res      this chunk's residual fragment (residual_prefetch), ignored unless the mode adds one
+//   bias_s   this chunk's 32 bias values in shared memory (staged per tile), ignored unless e.bias
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, int g, int m_slab, int n, float* v, uint8_t* stg,
+                                               int lane, const float4 (&res)[8], const float* bias_s) {
+  const int N = e.N, M = e.M;
+  const bool has_rowvec = MODE == EPI_GENERIC && e.rowvec != nullptr;
+  const bool has_res = MODE == EPI_RESIDUAL || (MODE == EPI_GENERIC && e.residual != nullptr);
+  const bool remap = MODE == EPI_GENERIC && e.rows_in > 0;
+  const bool stage16 = MODE == EPI_RESIDUAL ? false : (e.out_dtype != SVIT_F32 && !has_rowvec && !has_res);
+  const int jj = lane & 7, rsub = lane >> 3;  // coalesced fp32 layout: 4 rows x 8 float4 per warp access
+
+  if (e.bias) {  // broadcast reads of the staged bias: no global-load latency on the chunk's critical path
+    float4 t[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 8; ++i) t[i] = reinterpret_cast<const float4*>(bias_s)[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(t[i].x, t[i].y));
+      const float2 b = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(t[i].z, t[i].w));
+      v[4 * i] = a.x, v[4 * i + 1] = a.y, v[4 * i + 2] = b.x, v[4 * i + 3] = b.y;
     }
-    if (e.rowvec) {
-      const float4* b = reinterpret_cast<const float4*>(e.rowvec + (size_t)g * e.rowvec_gs + (size_t)(orow % e.rows_out) * N + n);
+  }
+  if (MODE != EPI_RESIDUAL && e.gelu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 t = __ldg(b + i);
-        v[4 * i] += t.x, v[4 * i + 1] += t.y, v[4 * i + 2] += t.z, v[4 * i + 3] += t.w;
-      }
-    }
-    if (e.residual) {
-      const float4* b = reinterpret_cast<const float4*>(e.residual + (size_t)g * e.residual_gs + (size_t)orow * N + n);
+    for (int i = 0; i < 32; i += 2) gelu_pair(v[i], v[i + 1]);
+  }
+
+  if (stage16) {
+    // 16-bit tile: rows of 64 bytes, 16-byte chunk j of row r at chunk (j ^ ((r >> 1) & 3))
+    uint32_t w[16];
+    if (e.out_dtype == SVIT_BF16) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 t = b[i];
-        v[4 * i] += t.x, v[4 * i + 1] += t.y, v[4 * i + 2] += t.z, v[4 * i + 3] += t.w;
-      }
-    }
-    const size_t idx = (size_t)g * e.out_gs + (size_t)orow * N + n;
-    if (e.out_dtype == SVIT_F32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + idx);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else if (e.out_dtype == SVIT_BF16) {
-      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + idx);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                          pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
     } else {
-      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(e.out) + idx);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+    }
+    uint8_t* wbase = stg + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(wbase + ((j ^ sw) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+    __syncwarp();
+    const int ch = lane & 3;
+    uint4 q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // 8 rows per access, 4 lanes cover one 64-byte row segment
+      const int rr = i * 8 + (lane >> 2);
+      q[i] = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+    }
+    uint16_t* out = reinterpret_cast<uint16_t*>(e.out) + (size_t)g * e.out_gs + n + ch * 8;
+    if (remap) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = m_slab + i * 8 + (lane >> 2);
+        if (row < M) *reinterpret_cast<uint4*>(out + (size_t)epi_out_row(e, row) * N) = q[i];
+      }
+    } else {
+      uint16_t* o = out + (size_t)(m_slab + (lane >> 2)) * N;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
-        o[i] = make_uint4(pack_f16x2_sat(v[8 * i], v[8 * i + 1]), pack_f16x2_sat(v[8 * i + 2], v[8 * i + 3]),
-                          pack_f16x2_sat(v[8 * i + 4], v[8 * i + 5]), pack_f16x2_sat(v[8 * i + 6], v[8 * i + 7]));
+        if (m_slab + i * 8 + (lane >> 2) < M) *reinterpret_cast<uint4*>(o + (size_t)(i * 8) * N) = q[i];
     }
-  } else {  // ragged N: element-wise (static indices keep v[] in registers)
+  } else {
+    // fp32 tile: rows of 128 bytes, 16-byte chunk j of row r at chunk (j ^ (r & 7))
+    uint8_t* wbase = stg + lane * 128;
+    const int sw = lane & 7;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (n + i < N) epi_store(e, g, orow, n + i, epi_apply(e, g, orow, n + i, v[i]));
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(wbase + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const size_t base = (size_t)g * e.out_gs + n + jj * 4;
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {  // two batches of 4 row groups: loads first, then adds + stores
+      float4 q[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rr = (hb * 4 + k) * 4 + rsub;
+        q[k] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((jj ^ (rr & 7)) << 4));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = hb * 4 + k;
+        const int row = m_slab + i * 4 + rsub;
+        if (row < M) {
+          const int64_t orow = remap ? epi_out_row(e, row) : (int64_t)row;
+          if (has_rowvec) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(e.rowvec + (size_t)g * e.rowvec_gs +
+                                                                   (size_t)(orow % e.rows_out) * N + n + jj * 4));
+            q[k].x += t.x, q[k].y += t.y, q[k].z += t.z, q[k].w += t.w;
+          }
+          if (has_res) q[k].x += res[i].x, q[k].y += res[i].y, q[k].z += res[i].z, q[k].w += res[i].w;
+          const size_t idx = base + (size_t)orow * N;
+          if (MODE == EPI_RESIDUAL || e.out_dtype == SVIT_F32)
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + idx) = q[k];
+          else if (e.out_dtype == SVIT_BF16)
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + idx) =
+                make_uint2(pack_bf16x2(q[k].x, q[k].y), pack_bf16x2(q[k].z, q[k].w));
+          else
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(e.out) + idx) =
+                make_uint2(pack_f16x2_sat(q[k].x, q[k].y), pack_f16x2_sat(q[k].z, q[k].w));
+        }
+      }
+    }
+  }
+  __syncwarp();  // the staging tile is rewritten by the next chunk
+}
+
+// ragged N (not a multiple of 8, or a partial last chunk): element-wise in the row layout
+__device__ __forceinline__ void epilogue_row_ragged(const EpiArgs& e, int g, int r, int n, const float* v) {
+  const int64_t orow = epi_out_row(e, r);
+#pragma unroll
+  for (int i = 0; i < 32; ++i)  // static indices keep v[] in registers
+    if (n + i < e.N) epi_store(e, g, orow, n + i, epi_apply(e, g, orow, n + i, v[i]));
+}
+
+// ---- epilogue of one 128 x BN accumulator tile by one epilogue warp ---------------------------
+// The warp owns TMEM lanes 32*quarter.. (rows m_slab..m_slab+31) and columns half*BN/2.. of the tile.
+// Everything that comes from global memory is requested BEFORE it is needed: the tile's bias slice
+// goes to shared memory and the first residual fragment to registers before the wait on the
+// accumulator, each further residual fragment one chunk ahead.  (With the loads issued where they
+// are used, an L2 round trip per chunk sat on the epilogue's critical path and the tensor pipe
+// idled a third of the time: profiles/r03_gemm_qkv.)
+template <int BN, int MODE, class Arrive>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape& sh, int g, int m_slab, int n0, int half,
+                                              int lane, uint32_t tmem_acc, uint8_t* stg, float* bias_s,
+                                              uint64_t* tfull, uint32_t parity, Arrive arrive) {
+  constexpr int NCH = BN / 64;  // 32-column chunks per warp (2 or 4)
+  const bool vec_ok = (sh.N & 7) == 0;
+  const int n_w = n0 + half * (BN / 2);
+  const bool rows_ok = m_slab < sh.M;
+  if (epi.bias && vec_ok) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane * 4 < BN / 2 && n_w + lane * 4 < sh.N)
+      b = __ldg(reinterpret_cast<const float4*>(epi.bias + (size_t)g * epi.bias_gs + n_w + lane * 4));
+    reinterpret_cast<float4*>(bias_s)[lane] = b;
+    __syncwarp();
+  }
+  const bool use_res = (MODE == EPI_RESIDUAL || (MODE == EPI_GENERIC && epi.residual)) && vec_ok && rows_ok;
+  float4 res0[8], res1[8];
+  if (use_res && n_w + 32 <= sh.N) residual_prefetch<MODE>(epi, g, m_slab, n_w, lane, res0);
+  mbar_wait(tfull, parity);
+  tc_fence_after();
+  // Two chunks per trip, so that the TMEM load and the residual reads of the next chunk are in
+  // flight under the math and the stores of the current one.
+  float v0[32], v1[32];
+  const uint32_t t0 = tmem_acc + (uint32_t)(half * (BN / 2));
+  tmem_ld_32x32_issue(t0, v0);
+  auto chunk = [&](int n, float* v, const float4 (&res)[8], int c) {
+    if (n < sh.N && rows_ok) {
+      if (vec_ok && n + 32 <= sh.N)
+        epilogue_chunk<MODE>(epi, g, m_slab, n, v, stg, lane, res, bias_s + 32 * c);
+      else if (m_slab + lane < sh.M)
+        epilogue_row_ragged(epi, g, m_slab + lane, n, v);
+    }
+  };
+#pragma unroll 1
+  for (int c = 0; c < NCH; c += 2) {
+    const int n = n_w + c * 32;
+    tmem_ld_wait();
+    tmem_ld_32x32_issue(t0 + (uint32_t)((c + 1) * 32), v1);
+    if (use_res && n + 64 <= sh.N) residual_prefetch<MODE>(epi, g, m_slab, n + 32, lane, res1);
+    chunk(n, v0, res0, c);
+    tmem_ld_wait();
+    if (c + 2 < NCH) {
+      tmem_ld_32x32_issue(t0 + (uint32_t)((c + 2) * 32), v0);
+      if (use_res && n + 96 <= sh.N) residual_prefetch<MODE>(epi, g, m_slab, n + 64, lane, res0);
+    } else {  // accumulator drained into registers: hand the TMEM buffer back early
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive();
+    }
+    chunk(n + 32, v1, res1, c + 1);
   }
 }
 
 // ---- the kernel --------------------------------------------------------------------------
-template <int BN, int KIND>
+template <int BN, int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                    const TcShape sh, const EpiArgs epi, const uint32_t idesc) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB aligned, still a __shared__ pointer
+  uint8_t* staging = smem + (size_t)C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -227,70 +510,66 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int64_t tiles_per_group = (int64_t)sh.tiles_m * sh.tiles_n;
 
-  if (warp == 0) {
-    if (lane == 0) {  // ===== TMA producer =====
-      int s = 0;
-      uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
-        const int g = (int)(tile / tiles_per_group);
-        const int rem = (int)(tile % tiles_per_group);
-        const int m0 = (rem / sh.tiles_n) * BM, n0 = (rem % sh.tiles_n) * BN;
-        for (int kb = 0; kb < sh.num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+  if (warp == 0) {  // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
+      const int g = (int)(tile / tiles_per_group);
+      const int rem = (int)(tile % tiles_per_group);
+      const int m0 = (rem / sh.tiles_n) * BM, n0 = (rem % sh.tiles_n) * BN;
+      for (int kb = 0; kb < sh.num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           const int k0 = kb * (KIND == 0 ? 64 : 32);
           tma_load_3d(sa, &tma_a, &full_bar[s], k0, m0, sh.a_grouped ? g : 0);
           tma_load_3d(sa + C::A_BYTES, &tma_b, &full_bar[s], k0, n0, g);
-          if (++s == C::STAGES) s = 0, ph ^= 1;
         }
+        __syncwarp();
+        if (++s == C::STAGES) s = 0, ph ^= 1;
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ===== MMA issuer =====
-      int s = 0, acc = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], aph ^ 1);
+  } else if (warp == 1) {  // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+    int s = 0, acc = 0;
+    uint32_t ph = 0, aph = 0;
+    const uint64_t adesc0 = umma_desc(smem_u32(smem)), bdesc0 = umma_desc(smem_u32(smem) + C::A_BYTES);
+    for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < sh.num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < sh.num_kb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + C::A_BYTES;
+        if (elect_one()) {
+          const uint64_t ad = umma_desc_advance(adesc0, (uint32_t)s * C::STAGE_BYTES);
+          const uint64_t bd = umma_desc_advance(bdesc0, (uint32_t)s * C::STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x 32 bytes along K inside the 128-byte swizzle span
-            tc_mma<KIND>(d_tmem, umma_desc(a_addr + k * 32), umma_desc(b_addr + k * 32), idesc, (uint32_t)(kb | k));
+            tc_mma<KIND>(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (uint32_t)(kb | k));
           tc_commit(&empty_bar[s]);  // smem stage reusable once these MMAs have read it
-          if (++s == C::STAGES) s = 0, ph ^= 1;
+          if (kb == sh.num_kb - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
         }
-        tc_commit(&tfull_bar[acc]);  // accumulator complete
-        if ((acc ^= 1) == 0) aph ^= 1;
+        __syncwarp();
+        if (++s == C::STAGES) s = 0, ph ^= 1;
       }
+      if ((acc ^= 1) == 0) aph ^= 1;
     }
   } else {  // ===== epilogue warps =====
     const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31 are accessible to this warp
     const int half = (warp - 2) >> 2;        // which half of the tile's columns
+    uint8_t* stg = staging + (size_t)(warp - 2) * kStagingPerWarp;
+    float* bias_s = reinterpret_cast<float*>(staging + (size_t)kEpiWarps * kStagingPerWarp + (size_t)(warp - 2) * kBiasPerWarp);
     int acc = 0;
     uint32_t aph = 0;
     for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
       const int g = (int)(tile / tiles_per_group);
       const int rem = (int)(tile % tiles_per_group);
       const int m0 = (rem / sh.tiles_n) * BM, n0 = (rem % sh.tiles_n) * BN;
-      mbar_wait(&tfull_bar[acc], aph);
-      tc_fence_after();
-      const int r = m0 + quarter * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int col = half * (BN / 2) + c * 32;
-        float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col), v);
-        if (r < sh.M && n0 + col < sh.N) epilogue_row32(epi, g, r, n0 + col, v);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      uint64_t* te = &tempty_bar[acc];
+      epilogue_tile<BN, MODE>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
+                        tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), stg, bias_s, &tfull_bar[acc], aph,
+                        [te] { mbar_arrive(te); });
       if ((acc ^= 1) == 0) aph ^= 1;
     }
   }
@@ -299,6 +578,147 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ---- the CTA-pair kernel (cta_group::2) ----------------------------------------------------
+template <int STAGES_>
+struct Cfg2 {
+  static constexpr int BN = 256;                    // N of the pair tile; each CTA stages BN / 2 rows of B
+  static constexpr int STAGES = STAGES_;
+  static constexpr int A_BYTES = BM * 128;          // this CTA's 128 rows of A, one 128-byte k-block
+  static constexpr int B_BYTES = (BN / 2) * 128;    // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int NUM_BARS = 2 * STAGES + 4;
+  static constexpr int STAGING_BYTES = kEpiWarps * (kStagingPerWarp + kBiasPerWarp);
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int KIND, int STAGES, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const TcShape sh, const EpiArgs epi, const uint32_t idesc) {
+  using C = Cfg2<STAGES>;
+  constexpr int BN = C::BN;
+  extern __shared__ uint8_t smem_raw[];
+  // identical carve-up in both CTAs: the pair MMA and the multicast commits address the peer's
+  // shared memory by the SAME offsets
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB aligned, still a __shared__ pointer
+  uint8_t* staging = smem + (size_t)C::STAGES * C::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + C::STAGING_BYTES);  // used in the leader only
+  uint64_t* empty_bar = full_bar + C::STAGES;                                    // per CTA
+  uint64_t* tfull_bar = empty_bar + C::STAGES;                                   // per CTA
+  uint64_t* tempty_bar = tfull_bar + 2;                                          // used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // the leader's producer arrives once and expects both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);               // one multicast tcgen05.commit
+      mbar_init(&tempty_bar[a], 2 * kEpiWarps);  // the epilogue warps of BOTH CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // one warp of each CTA, same warp id, same destination offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t tiles_per_group = (int64_t)sh.tiles_m * sh.tiles_n;
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {  // ===== TMA producer (both CTAs; warp-uniform loop, one elected lane issues) =====
+    const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's full barriers
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t tile = pair; tile < sh.total_tiles; tile += npairs) {
+      const int g = (int)(tile / tiles_per_group);
+      const int rem = (int)(tile % tiles_per_group);
+      const int m0 = (rem / sh.tiles_n) * (2 * BM) + (int)rank * BM;
+      const int n0 = (rem % sh.tiles_n) * BN + (int)rank * (BN / 2);
+      for (int kb = 0; kb < sh.num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
+          const int k0 = kb * (KIND == 0 ? 64 : 32);
+          tma_load_3d_pair(sa, &tma_a, full0 + 8u * s, k0, m0, sh.a_grouped ? g : 0);
+          tma_load_3d_pair(sa + C::A_BYTES, &tma_b, full0 + 8u * s, k0, n0, g);
+        }
+        __syncwarp();
+        if (++s == C::STAGES) s = 0, ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {  // ===== MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues) =====
+      int s = 0, acc = 0;
+      uint32_t ph = 0, aph = 0;
+      const uint64_t adesc0 = umma_desc(smem_u32(smem)), bdesc0 = umma_desc(smem_u32(smem) + C::A_BYTES);
+      for (int64_t tile = pair; tile < sh.total_tiles; tile += npairs) {
+        mbar_wait(&tempty_bar[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < sh.num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = umma_desc_advance(adesc0, (uint32_t)s * C::STAGE_BYTES);
+            const uint64_t bd = umma_desc_advance(bdesc0, (uint32_t)s * C::STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_pair<KIND>(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (uint32_t)(kb | k));
+            tc_commit_pair(&empty_bar[s]);  // frees stage s in both CTAs
+            if (kb == sh.num_kb - 1) tc_commit_pair(&tfull_bar[acc]);  // both CTAs' halves of the accumulator are complete
+          }
+          __syncwarp();
+          if (++s == C::STAGES) s = 0, ph ^= 1;
+        }
+        if ((acc ^= 1) == 0) aph ^= 1;
+      }
+    }
+  } else {  // ===== epilogue warps (both CTAs, each its own 128 rows) =====
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* stg = staging + (size_t)(warp - 2) * kStagingPerWarp;
+    float* bias_s = reinterpret_cast<float*>(staging + (size_t)kEpiWarps * kStagingPerWarp + (size_t)(warp - 2) * kBiasPerWarp);
+    const uint32_t tempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+    int acc = 0;
+    uint32_t aph = 0;
+    for (int64_t tile = pair; tile < sh.total_tiles; tile += npairs) {
+      const int g = (int)(tile / tiles_per_group);
+      const int rem = (int)(tile % tiles_per_group);
+      const int m0 = (rem / sh.tiles_n) * (2 * BM) + (int)rank * BM, n0 = (rem % sh.tiles_n) * BN;
+      const uint32_t te = tempty0 + 8u * acc;
+      epilogue_tile<BN, MODE>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
+                        tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), stg, bias_s, &tfull_bar[acc], aph,
+                        [te] { mbar_arrive_cluster(te); });
+      if ((acc ^= 1) == 0) aph ^= 1;
+    }
+  }
+  // Nobody leaves while the peer may still multicast a commit into, or read operands from, this
+  // CTA's shared memory; TMEM is released by both CTAs after that.
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
   }
 }
@@ -350,12 +770,37 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcShape sh, const Ep
   sh.tiles_m = (sh.M + BM - 1) / BM;
   sh.tiles_n = (sh.N + BN - 1) / BN;
   sh.total_tiles = (int64_t)sh.G * sh.tiles_m * sh.tiles_n;
-  auto kern = gemm_tc_kernel<BN, KIND>;
+  auto kern = gemm_tc_kernel<BN, KIND, EPI_GENERIC>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   const int64_t grid = std::min<int64_t>(sh.total_tiles, sm_count());
   kern<<<(unsigned)grid, kThreads, C::SMEM, stream>>>(ma, mb, sh, epi, idesc);
   SVIT_LAUNCH_CHECK("gemm_tc_kernel");
   return SVIT_OK;
+}
+
+template <int KIND, int STAGES, int MODE>
+int launch_tc2s(const CUtensorMap& ma, const CUtensorMap& mb, TcShape sh, const EpiArgs& epi, uint32_t idesc,
+                cudaStream_t stream) {
+  using C = Cfg2<STAGES>;
+  sh.tiles_m = (sh.M + 2 * BM - 1) / (2 * BM);
+  sh.tiles_n = sh.N / C::BN;
+  sh.total_tiles = (int64_t)sh.G * sh.tiles_m * sh.tiles_n;
+  auto kern = gemm_tc2_kernel<KIND, STAGES, MODE>;
+  SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  const int64_t npairs = std::min<int64_t>(sh.total_tiles, sm_count() / 2);
+  kern<<<(unsigned)(2 * npairs), kThreads, C::SMEM, stream>>>(ma, mb, sh, epi, idesc);
+  SVIT_LAUNCH_CHECK("gemm_tc2_kernel");
+  return SVIT_OK;
+}
+
+template <int KIND>
+int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const TcShape& sh, const EpiArgs& epi, uint32_t idesc,
+               cudaStream_t stream) {
+  const bool remap = epi.rows_in > 0;
+  if (!epi.rowvec && !epi.residual && !remap) return launch_tc2s<KIND, 5, EPI_DIRECT>(ma, mb, sh, epi, idesc, stream);
+  if (!epi.rowvec && epi.residual && !remap && !epi.gelu && epi.out_dtype == SVIT_F32)
+    return launch_tc2s<KIND, 5, EPI_RESIDUAL>(ma, mb, sh, epi, idesc, stream);
+  return launch_tc2s<KIND, 5, EPI_GENERIC>(ma, mb, sh, epi, idesc, stream);
 }
 
 }  // namespace
@@ -368,21 +813,34 @@ int gemm_tc(int precision, const void* A, int64_t a_gs, const void* B, int64_t b
   const int es = dtype_size(dtype);
   if (!aligned16(A) || !aligned16(B) || ((int64_t)K * es) % 16 || (a_gs * es) % 16 || (b_gs * es) % 16)
     SVIT_FAIL(SVIT_ERR_ALIGN, "gemm_tc: operands must be 16-byte aligned with K*elt and group strides multiples of 16 bytes");
-  if (epi.bias && !aligned16(epi.bias)) SVIT_FAIL(SVIT_ERR_ALIGN, "gemm_tc: bias must be 16-byte aligned");
+  if (N % 8 == 0) {  // the vectorised epilogue moves 16-byte pieces of bias / rowvec / residual / out
+    const int oes = dtype_size(epi.out_dtype);
+    if ((epi.bias && (!aligned16(epi.bias) || epi.bias_gs % 4)) || (epi.rowvec && (!aligned16(epi.rowvec) || epi.rowvec_gs % 4)) ||
+        (epi.residual && (!aligned16(epi.residual) || epi.residual_gs % 4)) || !aligned16(epi.out) || (epi.out_gs * oes) % 16)
+      SVIT_FAIL(SVIT_ERR_ALIGN, "gemm_tc: bias/rowvec/residual/out must be 16-byte aligned with 16-byte group strides");
+  }
   const int BN = (N % 256 == 0) ? 256 : 128;
+  static const bool no_pair = [] { const char* e = getenv("SVIT_GEMM_NO_PAIR"); return e && e[0] == '1'; }();
+  const bool pair = BN == 256 && M >= 2 * BM && !no_pair;  // CTA-pair kernel: each CTA stages half of the B tile
   CUtensorMap ma, mb;
   int rc;
   if ((rc = make_map(&ma, dtype, A, M, K, a_gs ? G : 1, a_gs, BM))) return rc;
-  if ((rc = make_map(&mb, dtype, B, N, K, b_gs ? G : 1, b_gs, BN))) return rc;
+  if ((rc = make_map(&mb, dtype, B, N, K, b_gs ? G : 1, b_gs, pair ? BN / 2 : BN))) return rc;
   TcShape sh{};
   sh.G = G, sh.M = M, sh.N = N, sh.K = K;
   const int bk = 128 / es;
   sh.num_kb = (K + bk - 1) / bk;
   sh.a_grouped = a_gs ? 1 : 0;
+  static const int flags = [] { const char* e = getenv("SVIT_GEMM_FLAGS"); return e ? atoi(e) : 0; }();
+  sh.flags = flags;
   SVIT_CHECK_ARG(b_gs != 0 || G == 1, "gemm_tc: B must be grouped when G > 1");
   // instruction descriptor: D fp32, A/B format, both K-major, N, M
   const uint32_t fmt = precision == SVIT_PREC_TF32 ? 2u : precision == SVIT_PREC_BF16 ? 1u : 0u;
-  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
+                         ((uint32_t)((pair ? 2 * BM : BM) >> 4) << 24);
+  if (pair)
+    return precision == SVIT_PREC_TF32 ? launch_tc2<1>(ma, mb, sh, epi, idesc, stream)
+                                       : launch_tc2<0>(ma, mb, sh, epi, idesc, stream);
   if (precision == SVIT_PREC_TF32)
     return BN == 256 ? launch_tc<256, 1>(ma, mb, sh, epi, idesc, stream) : launch_tc<128, 1>(ma, mb, sh, epi, idesc, stream);
   return BN == 256 ? launch_tc<256, 0>(ma, mb, sh, epi, idesc, stream) : launch_tc<128, 0>(ma, mb, sh, epi, idesc, stream);

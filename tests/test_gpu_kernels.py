@@ -196,7 +196,9 @@ def test_gemm_cuda_core_fp32(ops, G, M, N, K):
 
 
 TC_SHAPES = [(1, 128, 256, 64), (1, 128, 128, 64), (2, 300, 768, 768), (3, 197 * 4, 2304, 768),
-             (2, 640, 192, 192), (2, 640, 576, 192), (1, 1000, 768, 3072), (2, 130, 384, 384)]
+             (2, 640, 192, 192), (2, 640, 576, 192), (1, 1000, 768, 3072), (2, 130, 384, 384),
+             # CTA-pair (cta_group::2) kernel: N % 256 == 0 and M >= 256; ragged M, > 74 tiles per launch
+             (1, 256, 256, 64), (2, 257, 512, 136), (2, 6000, 768, 256), (1, 384, 3072, 768)]
 
 
 @pytest.mark.parametrize("prec_name", ["f16", "bf16", "tf32"])
