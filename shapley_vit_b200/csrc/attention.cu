@@ -132,8 +132,15 @@ int attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, int 
     const char* e = getenv("SVIT_ATTENTION_SIMT");
     return e && e[0] == '1';
   }();
-  if (!force_simt && head_dim == 64 && (dtype == SVIT_F16 || dtype == SVIT_BF16) && (heads * head_dim) % 8 == 0)
+  if (!force_simt && head_dim == 64 && (dtype == SVIT_F16 || dtype == SVIT_BF16) && (heads * head_dim) % 8 == 0) {
+    // 128 < T <= 256 (ViT at 224 px): tcgen05 / TMEM kernel; shorter sequences: warp-level MMA kernel
+    static const bool no_tc = [] {
+      const char* e = getenv("SVIT_ATTENTION_MMA_SYNC");
+      return e && e[0] == '1';
+    }();
+    if (Tn > 128 && !no_tc) return attention_tc(qkv, ctx, dtype, n_seq, Tn, heads, stream);
     return attention_mma(qkv, ctx, dtype, n_seq, Tn, heads, stream);
+  }
   switch (dtype) {
     case SVIT_F32: return dispatch_d<float>(qkv, ctx, n_seq, Tn, heads, head_dim, stream);
     case SVIT_BF16: return dispatch_d<__nv_bfloat16>(qkv, ctx, n_seq, Tn, heads, head_dim, stream);

@@ -16,6 +16,7 @@ int head(const float* X, int64_t x_gs, const float* wvec, int64_t vec_stride, in
          int64_t off_w, int64_t off_hb, float* logits, int64_t logits_stride, int G, int B, int T, int h, int n_cls,
          float eps, cudaStream_t stream);
 int attention_mma(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, cudaStream_t stream);
+int attention_tc(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, cudaStream_t stream);
 int attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, int head_dim,
               cudaStream_t stream);
 

@@ -33,6 +33,7 @@
 #include <cstdlib>
 
 #include "epilogue.cuh"
+#include "tma_util.h"
 
 namespace svit {
 namespace {
@@ -724,43 +725,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 }
 
 // ---- host side ----------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    else
-      cudaGetLastError();
-  }
-  return fn;
-}
-
 // 3-D map over a [groups, rows, K] K-contiguous operand; box = 128 bytes of K x box_rows rows.
 int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t K, int64_t groups, int64_t gs,
              int box_rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) SVIT_FAIL(SVIT_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int es = dtype_size(dtype);
-  CUtensorMapDataType dt = dtype == SVIT_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-                           : dtype == SVIT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                                : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)groups};
-  cuuint64_t gstr[2] = {(cuuint64_t)K * es, (cuuint64_t)(groups > 1 ? gs : rows * K) * es};
-  cuuint32_t box[3] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, dt, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) SVIT_FAIL(SVIT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return SVIT_OK;
+  return encode_map_3d(map, dtype, base, (uint64_t)K, (uint64_t)rows, (uint64_t)groups, (uint64_t)K * es,
+                       (uint64_t)(groups > 1 ? gs : rows * K) * es, (uint32_t)(128 / es), (uint32_t)box_rows);
 }
 
 template <int BN, int KIND>

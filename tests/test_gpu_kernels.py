@@ -161,6 +161,20 @@ def test_attention_fp32(ops, T, heads, d):
         assert (got16 - want16).abs().max() < tol
 
 
+@pytest.mark.parametrize("T,heads,n_seq", [(197, 12, 40), (129, 3, 5), (256, 2, 7), (144, 1, 300), (250, 4, 3)])
+@pytest.mark.parametrize("dt,tol", [(torch.float16, 4e-3), (torch.bfloat16, 3e-2)])
+def test_attention_tcgen05(ops, T, heads, n_seq, dt, tol):
+    """128 < T <= 256, head_dim 64: the tcgen05 / TMEM kernel (attention_tc.cu) vs fp32 softmax attention."""
+    d = 64
+    h = heads * d
+    q16 = gen(n_seq, T, 3 * h, seed=T + n_seq).to(dt)
+    q, k, v = (t_.float().view(n_seq, T, heads, d).transpose(1, 2) for t_ in q16.split(h, dim=2))
+    want = (torch.softmax(q @ k.transpose(2, 3) * d ** -0.5, dim=-1) @ v).transpose(1, 2).reshape(n_seq, T, h)
+    got = ops.attention(q16.cuda(), heads).cpu().float()
+    err = (got - want).abs().max().item()
+    assert err < tol, f"max err {err}"
+
+
 # ----------------------------------------------------------------------------- GEMM
 def ref_gemm(A, B, bias=None, residual=None, gelu=False, rowvec=None, rows_in=0, rows_out=0, row_shift=0):
     G = B.shape[0]
