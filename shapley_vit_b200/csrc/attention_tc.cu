@@ -166,6 +166,14 @@ template <typename T> __device__ __forceinline__ uint32_t pack16(float lo, float
 template <> __device__ __forceinline__ uint32_t pack16<__half>(float lo, float hi) { return pack_f16x2_sat(lo, hi); }
 template <> __device__ __forceinline__ uint32_t pack16<__nv_bfloat16>(float lo, float hi) { return pack_bf16x2(lo, hi); }
 
+// Debug aid (scripts/attn_trace.py): when set, CTA 0 records clock64() per phase of its first items.
+__device__ long long* g_att_trace = nullptr;
+constexpr int kTraceItems = 24, kTraceSlots = 16;
+#define ATT_TRACE(slot)                                                                      \
+  do {                                                                                       \
+    if (trace && lane == 0 && it < kTraceItems) trace[it * kTraceSlots + (slot)] = clock64(); \
+  } while (0)
+
 struct AttShape {
   int T, NK, heads;      // tokens, keys padded to a multiple of 16, heads
   int64_t items;         // n_seq * heads
@@ -173,19 +181,23 @@ struct AttShape {
   uint32_t idesc_qk, idesc_pv;
 };
 
-// One 32- (or, W16, 16-) column chunk of the softmax's second pass: p = 2^(s * sl2 - off) for the thread's
-// row, accumulated into `sum`, written back as 16-bit pairs over the first half of the chunk's own
-// columns.  MASK: keys >= Tn (only possible in the last chunk) contribute 0.
-template <typename T, bool W16, bool MASK>
-__device__ __forceinline__ void softmax_chunk(uint32_t tbuf, int c0, int Tn, float sl2, float noff, float2 (&sum)[2]) {
-  constexpr int W = W16 ? 16 : 32;
-  uint32_t r[32];
+// issue the TMEM load of the 32- (W16: 16-) column chunk at column c0 of the thread's row
+template <bool W16>
+__device__ __forceinline__ void chunk_load(uint32_t tbuf, int c0, uint32_t (&r)[32]) {
   if (W16) {
     TMEM_LD_X16(tbuf + (uint32_t)c0, r);
   } else {
     TMEM_LD_X32(tbuf + (uint32_t)c0, r);
   }
-  tmem_ld_wait();
+}
+
+// second pass on one loaded chunk: p = 2^(s * sl2 + noff) accumulated into `sum` and written back as
+// 16-bit pairs over the first half of the chunk's own columns.  MASK: keys >= Tn (only possible in
+// the last chunk) contribute 0.
+template <typename T, bool W16, bool MASK>
+__device__ __forceinline__ void chunk_exp(uint32_t tbuf, int c0, int Tn, float sl2, float noff, const uint32_t (&r)[32],
+                                          float2 (&sum)[2]) {
+  constexpr int W = W16 ? 16 : 32;
   uint32_t w[16];
   const float2 sc = make_float2(sl2, sl2), of = make_float2(noff, noff);
 #pragma unroll
@@ -203,25 +215,84 @@ __device__ __forceinline__ void softmax_chunk(uint32_t tbuf, int c0, int Tn, flo
   if (!W16) TMEM_ST_X8(tbuf + (uint32_t)(c0 >> 1) + 8, (w + 8));
 }
 
-// row maximum of one chunk (same shapes as softmax_chunk)
+// first pass on one loaded chunk: running row maxima (four independent chains: a single chain of
+// dependent FMNMX3 was ~800 cycles per row, profiles/r08 trace)
 template <bool W16, bool MASK>
-__device__ __forceinline__ float max_chunk(uint32_t tbuf, int c0, int Tn, float m) {
+__device__ __forceinline__ void chunk_max(int c0, int Tn, const uint32_t (&r)[32], float (&m)[4]) {
   constexpr int W = W16 ? 16 : 32;
-  uint32_t r[32];
-  if (W16) {
-    TMEM_LD_X16(tbuf + (uint32_t)c0, r);
-  } else {
-    TMEM_LD_X32(tbuf + (uint32_t)c0, r);
-  }
-  tmem_ld_wait();
-  if (MASK) {
 #pragma unroll
-    for (int i = 0; i < W; ++i)
-      if (c0 + i >= Tn) r[i] = 0xff800000u;  // -inf
+  for (int i = 0; i < W; i += 2) {
+    float a = __uint_as_float(r[i]), b = __uint_as_float(r[i + 1]);
+    if (MASK) {
+      if (c0 + i >= Tn) a = -INFINITY;
+      if (c0 + i + 1 >= Tn) b = -INFINITY;
+    }
+    m[(i >> 1) & 3] = fmax3(m[(i >> 1) & 3], a, b);
   }
+}
+
+// Softmax of the thread's row of S (NK columns at tbuf), P written in place; returns 1 / row sum.
+// Both passes run their TMEM loads one chunk ahead of the arithmetic (two register buffers), and the
+// first load of pass 2 is issued under the last maximum of pass 1: the load latency (not the MUFU
+// pipe) was what bounded the first version of this kernel.
+template <typename T, int NK>
+__device__ __forceinline__ float softmax_row(uint32_t tbuf, int Tn, float sl2, long long* mid_stamp) {
+  constexpr int NFULL = NK / 32;           // 32-column chunks
+  constexpr bool TAIL = (NK % 32) != 0;    // plus one 16-column chunk
+  constexpr int NCH = NFULL + (TAIL ? 1 : 0);
+  // only the LAST chunk can hold keys >= T (NK - 16 < T <= NK)
+  uint32_t ra[32], rb[32];
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  chunk_load<false>(tbuf, 0, ra);
 #pragma unroll
-  for (int i = 0; i < W; i += 2) m = fmax3(m, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-  return m;
+  for (int c = 0; c < NCH; ++c) {
+    uint32_t(&cur)[32] = (c & 1) ? rb : ra;
+    uint32_t(&nxt)[32] = (c & 1) ? ra : rb;
+    tmem_ld_wait();
+    if (c + 1 < NCH) {
+      if (TAIL && c + 1 == NCH - 1)
+        chunk_load<true>(tbuf, (c + 1) * 32, nxt);
+      else
+        chunk_load<false>(tbuf, (c + 1) * 32, nxt);
+    } else {
+      chunk_load<false>(tbuf, 0, nxt);  // pass 2, chunk 0
+    }
+    if (c == NCH - 1) {
+      if (TAIL)
+        chunk_max<true, true>(c * 32, Tn, cur, mx);
+      else
+        chunk_max<false, true>(c * 32, Tn, cur, mx);
+    } else {
+      chunk_max<false, false>(c * 32, Tn, cur, mx);
+    }
+  }
+  const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+  if (mid_stamp) *mid_stamp = clock64();
+  const float noff = -m * sl2;
+  float2 sum[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    // pass 1 left its extra load in the buffer pass-1 chunk NCH would have used
+    uint32_t(&cur)[32] = ((c + NCH) & 1) ? rb : ra;
+    uint32_t(&nxt)[32] = ((c + NCH) & 1) ? ra : rb;
+    tmem_ld_wait();
+    if (c + 1 < NCH) {
+      if (TAIL && c + 1 == NCH - 1)
+        chunk_load<true>(tbuf, (c + 1) * 32, nxt);
+      else
+        chunk_load<false>(tbuf, (c + 1) * 32, nxt);
+    }
+    if (c == NCH - 1) {
+      if (TAIL)
+        chunk_exp<T, true, true>(tbuf, c * 32, Tn, sl2, noff, cur, sum);
+      else
+        chunk_exp<T, false, true>(tbuf, c * 32, Tn, sl2, noff, cur, sum);
+    } else {
+      chunk_exp<T, false, false>(tbuf, c * 32, Tn, sl2, noff, cur, sum);
+    }
+  }
+  tmem_st_wait();
+  return 1.0f / ((sum[0].x + sum[0].y) + (sum[1].x + sum[1].y));
 }
 
 // NK: keys padded to a multiple of 16 (compile time: the softmax loops are fully unrolled)
@@ -241,6 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const trace = blockIdx.x == 0 ? g_att_trace : nullptr;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
@@ -284,42 +356,55 @@ __global__ void __launch_bounds__(kThreads, 1)
       __syncwarp();
     }
   } else if (warp == 1) {  // ===== MMA issuer =====
-    int it = 0;
+    // Issue order per item i:  S0(i), O1(i-1), S1(i), O0(i): the softmax groups run out of step, so one
+    // group's P V, O read-out and next Q K^T overlap the other group's exponentials.
     constexpr uint32_t nks = (uint32_t)NK / 16;
+    auto issue_qk = [&](uint32_t st, int b, uint32_t par) {  // S_b = Q_b K^T
+      mbar_wait(&s_free[b], par ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t qdesc = umma_desc(st + (uint32_t)b * 128 * 128), kdesc = umma_desc(st + kQBytes);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma_ss(tmem_base + (uint32_t)b * 256, qdesc + 2 * k, kdesc + 2 * k, sh.idesc_qk, (uint32_t)k);
+        tc_commit(&s_full[b]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](uint32_t st, int b, uint32_t par, uint64_t* stage_done) {  // O_b = P_b V
+      mbar_wait(&p_full[b], par);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t vdesc = umma_desc(st + kQBytes + kKVBytes);
+#pragma unroll
+        for (uint32_t j = 0; j < nks; ++j)  // 16 keys per instruction: 8 TMEM columns of P, 2 KB of V
+          mma_ts(tmem_base + (uint32_t)b * 256 + kOCol, tmem_base + (uint32_t)b * 256 + 8 * j, vdesc + 128 * j, sh.idesc_pv,
+                 j);
+        tc_commit(&o_full[b]);
+        if (stage_done) tc_commit(stage_done);  // every MMA reading this smem stage has been issued
+      }
+      __syncwarp();
+    };
+    int it = 0;
+    uint32_t st_prev = 0;
     for (int64_t item = blockIdx.x; item < sh.items; item += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t par = (uint32_t)it & 1;
       mbar_wait(&kv_full[s], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t st = smem_u32(smem + (size_t)s * kStageBytes);
-      const uint64_t kdesc = umma_desc(st + kQBytes), vdesc = umma_desc(st + kQBytes + kKVBytes);
-#pragma unroll 1
-      for (int b = 0; b < 2; ++b) {  // S_b = Q_b K^T
-        mbar_wait(&s_free[b], par ^ 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t qdesc = umma_desc(st + (uint32_t)b * 128 * 128);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            mma_ss(tmem_base + (uint32_t)b * 256, qdesc + 2 * k, kdesc + 2 * k, sh.idesc_qk, (uint32_t)k);
-          tc_commit(&s_full[b]);
-        }
-        __syncwarp();
-      }
-#pragma unroll 1
-      for (int b = 0; b < 2; ++b) {  // O_b = P_b V
-        mbar_wait(&p_full[b], par);
-        tc_fence_after();
-        if (elect_one()) {
-          for (uint32_t j = 0; j < nks; ++j)  // 16 keys per instruction: 8 TMEM columns of P, 2 KB of V
-            mma_ts(tmem_base + (uint32_t)b * 256 + kOCol, tmem_base + (uint32_t)b * 256 + 8 * j, vdesc + 128 * j,
-                   sh.idesc_pv, j);
-          tc_commit(&o_full[b]);
-          if (b == 1) tc_commit(&kv_empty[s]);  // every MMA reading this stage has been issued
-        }
-        __syncwarp();
-      }
+      ATT_TRACE(8);
+      issue_qk(st, 0, par);
+      ATT_TRACE(9);
+      if (it > 0) issue_pv(st_prev, 1, par ^ 1, &kv_empty[s ^ 1]);
+      ATT_TRACE(10);
+      issue_qk(st, 1, par);
+      ATT_TRACE(11);
+      issue_pv(st, 0, par, nullptr);
+      ATT_TRACE(12);
+      st_prev = st;
     }
+    if (it > 0) issue_pv(st_prev, 1, (uint32_t)(it - 1) & 1, &kv_empty[(it - 1) & 1]);
   } else {  // ===== softmax groups =====
     const int grp = (warp - 2) >> 2;   // tile / TMEM buffer / staging buffer of this group
     const int quarter = warp & 3;      // TMEM lanes 32 * quarter .. + 31
@@ -327,7 +412,6 @@ __global__ void __launch_bounds__(kThreads, 1)
     const uint32_t tbuf = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)grp * 256;
     uint8_t* ost = o_stage + (size_t)grp * kOBytes;
     const int row_in_tile = quarter * 32 + lane;
-    const int row = grp * 128 + row_in_tile;
     const bool warp_valid = grp * 128 + quarter * 32 < sh.T;
     const int Tn = sh.T;
     const float sl2 = sh.sl2;
@@ -336,38 +420,15 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t par = (uint32_t)it & 1;
       mbar_wait(&s_full[grp], par);
       tc_fence_after();
+      if (quarter == 0) ATT_TRACE(4 * grp + 0);
       float inv = 0.f;
-      if (warp_valid) {
-        constexpr int NFULL = NK / 32;           // 32-column chunks
-        constexpr bool TAIL = (NK % 32) != 0;    // plus one 16-column chunk
-        // Only the LAST chunk can hold keys >= T (NK - 16 < T <= NK).
-        // ---- pass 1: row maximum over the valid keys ----
-        float m = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < NFULL; ++c) {
-          if (!TAIL && c == NFULL - 1)
-            m = max_chunk<false, true>(tbuf, c * 32, Tn, m);
-          else
-            m = max_chunk<false, false>(tbuf, c * 32, Tn, m);
-        }
-        if (TAIL) m = max_chunk<true, true>(tbuf, NFULL * 32, Tn, m);
-        // ---- pass 2: p = 2^(s * sl2 - m * sl2), row sum, P -> TMEM (16-bit pairs, in place over S) ----
-        const float noff = -m * sl2;
-        float2 sum[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-#pragma unroll
-        for (int c = 0; c < NFULL; ++c) {
-          if (!TAIL && c == NFULL - 1)
-            softmax_chunk<T, false, true>(tbuf, c * 32, Tn, sl2, noff, sum);
-          else
-            softmax_chunk<T, false, false>(tbuf, c * 32, Tn, sl2, noff, sum);
-        }
-        if (TAIL) softmax_chunk<T, true, true>(tbuf, NFULL * 32, Tn, sl2, noff, sum);
-        inv = 1.0f / ((sum[0].x + sum[0].y) + (sum[1].x + sum[1].y));
-        tmem_st_wait();
-      }
+      if (warp_valid)
+        inv = softmax_row<T, NK>(tbuf, Tn, sl2,
+                                 (trace && quarter == 0 && lane == 0 && it < kTraceItems) ? trace + it * kTraceSlots + 13 + grp : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[grp]);
+      if (quarter == 0) ATT_TRACE(4 * grp + 1);
 
       // ---- O = P V is on its way: make the staging tile reusable meanwhile ----
       if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -375,6 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
       mbar_wait(&o_full[grp], par);
       tc_fence_after();
+      if (quarter == 0) ATT_TRACE(4 * grp + 2);
       uint32_t o[64];
       {
         uint32_t* o0 = o;
@@ -407,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         tma_store_3d(&map_o, ost, head * kD, grp * 128, seq);  // rows >= T are clipped by the tensor map
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      (void)row;
+      if (quarter == 0) ATT_TRACE(4 * grp + 3);
     }
     if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -461,6 +523,16 @@ int launch_att(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, int
 }
 
 }  // namespace
+
+// undocumented debug hook: device buffer of kTraceItems * kTraceSlots int64 (or NULL to switch tracing off)
+extern "C" int svit_debug_attention_trace(void* device_buffer) {
+  long long* p = static_cast<long long*>(device_buffer);
+  SVIT_CUDA(cudaMemcpyToSymbol(g_att_trace, &p, sizeof(p)));
+  return SVIT_OK;
+}
+
+namespace {
+}
 
 // 16-bit operands, head_dim 64, 128 < T <= 256, h % 8 == 0, 16-byte aligned qkv / ctx
 int attention_tc(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
