@@ -344,7 +344,7 @@ def run_ours(a):
     g_ms, g_flops, g_n = timing["gemm"]
     tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 grouped GEMM)" if a.precision != "f32" else "gemm_simt_kernel",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2 grouped GEMM)" if a.precision != "f32" else "gemm_simt_kernel",
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                 "peak_source": f"{peak_src}; sustained figure (kernel timed inside a long step); burst = {peaks['bf16_tflops']}",
                 "traffic": None, "launches": int(g_n), "avg_launch_ms": g_ms / max(g_n, 1),
