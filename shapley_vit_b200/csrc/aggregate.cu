@@ -20,6 +20,8 @@
 // which is bit-identical to the reference whenever frozenset(coalition) iterates in ascending
 // order.  Algorithmic bytes per launch:
 //   4*P*(N+1) + sizeof(out)*P*C.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace svit {
@@ -116,7 +118,9 @@ struct AggParams {
 };
 
 // dynamic smem: [STAGES][(N+1)][TILE] floats | ratio table | mask table | mbarriers [STAGES]
-template <typename OutT, int BLOCK>
+// PF: issue the loads of client j + 1 before the arithmetic of client j (pays when the kernel is
+// HBM-bound, C <= 8; costs issue slots when it is instruction-bound, C > 8)
+template <typename OutT, int BLOCK, bool PF>
 __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant__ AggParams p) {
   constexpr int TILE = BLOCK * kVec;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -195,18 +199,33 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
           for (int q = 0; q < 4; ++q) acc[cc][q] = make_float2(0.f, 0.f);
         const float4* rt = reinterpret_cast<const float4*>(s_ratio + (size_t)ch * N * kCChunk);
         const uint32_t* mk = s_mask + ch * N;
+        // the loads of client j + 1 (parameters, membership word, ratios) are issued before the
+        // arithmetic of client j, so their shared-memory latency is not on the branch at the loop top
+        float4 da = *reinterpret_cast<const float4*>(st + ea);
+        float4 db = *reinterpret_cast<const float4*>(st + eb);
+        uint32_t m = mk[0];
+        float4 r0 = rt[0], r1 = rt[1];
 #pragma unroll 1
         for (int j = 0; j < N; ++j) {
-          const float4 da = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + ea);
-          const float4 db = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + eb);
+          if (!PF) {
+            da = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + ea);
+            db = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + eb);
+            m = mk[j];
+            r0 = rt[2 * j], r1 = rt[2 * j + 1];
+          }
           const float2 d[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y),
                                make_float2(db.z, db.w)};
-          const uint32_t m = mk[j];
-          const float4 r0 = rt[2 * j], r1 = rt[2 * j + 1];
+          const uint32_t mc = m;
           const float r[kCChunk] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          if (PF && j + 1 < N) {
+            da = *reinterpret_cast<const float4*>(st + (size_t)(j + 1) * TILE + ea);
+            db = *reinterpret_cast<const float4*>(st + (size_t)(j + 1) * TILE + eb);
+            m = mk[j + 1];
+            r0 = rt[2 * j + 2], r1 = rt[2 * j + 3];
+          }
 #pragma unroll
           for (int cc = 0; cc < kCChunk; ++cc) {
-            if (m & (1u << cc)) {  // warp-uniform: a real branch skips the 8 packed operations
+            if (mc & (1u << cc)) {  // warp-uniform: a real branch skips the 4 packed products and the 8 sums
 #pragma unroll
               for (int q = 0; q < 4; ++q) acc[cc][q] = add2(acc[cc][q], mul2(r[cc], d[q]));
             }
@@ -248,7 +267,7 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
   }
 }
 
-template <typename OutT, int BLOCK>
+template <typename OutT, int BLOCK, bool PF>
 int launch(const AggParams& base, cudaStream_t stream) {
   AggParams p = base;
   constexpr int TILE = BLOCK * kVec;
@@ -269,7 +288,7 @@ int launch(const AggParams& base, cudaStream_t stream) {
   int per_sm = (int)(budget / (smem + 1024));  // +1 KB per-CTA reservation
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 8) per_sm = 8;
-  auto kern = aggregate_kernel<OutT, BLOCK>;
+  auto kern = aggregate_kernel<OutT, BLOCK, PF>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
@@ -278,11 +297,204 @@ int launch(const AggParams& base, cudaStream_t stream) {
   return SVIT_OK;
 }
 
+
+// ---- row-ring variant -------------------------------------------------------------------------
+// Same arithmetic, different staging: instead of holding all N+1 rows of a tile in shared memory
+// (whose footprint grows with N and costs occupancy: 0.50 of the copy peak at N = 16, 0.13 at
+// N = 64), a producer warp streams ONE 4 KB row-tile at a time through a ring of kRingSlots slots
+// and four consumer warps fold each row into their 8 coalition accumulators as it lands.  Shared
+// memory per CTA is independent of N.  For C > 8 the rows of a tile are streamed once per chunk of
+// 8 coalitions (the re-reads hit L2: the tile's rows were read a few microseconds earlier), and a
+// row none of the chunk's coalitions contains is not fetched at all.
+constexpr int kRingSlots = 8;
+constexpr int kRingConsumers = 128;                  // 4 warps x 8 parameters per thread
+constexpr int kRingTile = kRingConsumers * kVec;     // 1024 parameters = 4 KB per row-tile
+constexpr int kRingThreads = kRingConsumers + 32;    // + the producer warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// dynamic smem: [kRingSlots][kRingTile] floats | ratio table | mask table | full[kRingSlots] | empty[kRingSlots]
+template <typename OutT>
+__global__ void __launch_bounds__(kRingThreads) aggregate_ring_kernel(const __grid_constant__ AggParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int N = p.N, C = p.C;
+  const int nchunks = (C + kCChunk - 1) / kCChunk;
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  float* s_ratio = ring + (size_t)kRingSlots * kRingTile;
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_ratio + (size_t)nchunks * N * kCChunk);
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_mask + ((nchunks * N + 1) & ~1));
+  uint64_t* empty = full + kRingSlots;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < kRingSlots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kRingConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < nchunks * N * kCChunk; i += kRingThreads) s_ratio[i] = p.ratios[i];
+  for (int i = tid; i < nchunks * N; i += kRingThreads) s_mask[i] = p.masks[i];
+  __syncthreads();
+
+  const int64_t P = p.P;
+  const bool has_w0 = p.w0 != nullptr;
+  // Producer and consumers walk the same sequence: for tile, for chunk, for each row with a member in
+  // the chunk (ascending j), then the W_0 row.  A tile whose length is not a multiple of 4 floats (at
+  // most the last one) bypasses the ring: the consumers read it with guarded scalar loads.
+  if (tid >= kRingConsumers) {  // ===== producer warp =====
+    if (tid == kRingConsumers) {
+      uint32_t seq = 0;
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int len = (int)min((int64_t)kRingTile, P - t * kRingTile);
+        if (len & 3) continue;
+        const uint32_t bytes = (uint32_t)len * 4u;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          for (int j = 0; j <= N; ++j) {
+            const float* src;
+            if (j < N) {
+              if (s_mask[ch * N + j] == 0) continue;
+              src = p.deltas + (size_t)j * p.delta_stride + t * kRingTile;
+            } else {
+              if (!has_w0) continue;
+              src = p.w0 + t * kRingTile;
+            }
+            const uint32_t s = seq % kRingSlots;
+            mbar_wait(&empty[s], ((seq / kRingSlots) & 1) ^ 1);
+            mbar_expect_tx(&full[s], bytes);
+            bulk_g2s(ring + (size_t)s * kRingTile, src, bytes, &full[s]);
+            ++seq;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int lane = tid & 31;
+  const int ea = tid * 4, eb = kRingTile / 2 + tid * 4;  // two float4 per thread, each warp access contiguous
+  uint32_t seq = 0;
+  for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    const int len = (int)min((int64_t)kRingTile, P - t * kRingTile);
+    const bool ragged = (len & 3) != 0;
+    OutT* outp = reinterpret_cast<OutT*>(p.out) + t * kRingTile;
+#pragma unroll 1
+    for (int ch = 0; ch < nchunks; ++ch) {
+      float2 acc[kCChunk][4];
+#pragma unroll
+      for (int cc = 0; cc < kCChunk; ++cc)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[cc][q] = make_float2(0.f, 0.f);
+      float2 w[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float4* rt = reinterpret_cast<const float4*>(s_ratio + (size_t)ch * N * kCChunk);
+      const uint32_t* mk = s_mask + ch * N;
+#pragma unroll 1
+      for (int j = 0; j <= N; ++j) {
+        uint32_t m = 0;
+        const float* grow;
+        if (j < N) {
+          m = mk[j];
+          if (m == 0) continue;
+          grow = p.deltas + (size_t)j * p.delta_stride + t * kRingTile;
+        } else {
+          if (!has_w0) continue;
+          grow = p.w0 + t * kRingTile;
+        }
+        float4 da, db;
+        if (!ragged) {
+          const uint32_t s = seq % kRingSlots;
+          mbar_wait(&full[s], (seq / kRingSlots) & 1);
+          const float* st = ring + (size_t)s * kRingTile;
+          da = *reinterpret_cast<const float4*>(st + ea);
+          db = *reinterpret_cast<const float4*>(st + eb);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[s]);  // this warp has its copy of the slot in registers
+          ++seq;
+        } else {
+          float f[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            f[q] = ea + q < len ? grow[ea + q] : 0.f;
+            f[4 + q] = eb + q < len ? grow[eb + q] : 0.f;
+          }
+          da = make_float4(f[0], f[1], f[2], f[3]);
+          db = make_float4(f[4], f[5], f[6], f[7]);
+        }
+        const float2 d[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y),
+                             make_float2(db.z, db.w)};
+        if (j == N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[q] = d[q];
+        } else {
+          const float4 r0 = rt[2 * j], r1 = rt[2 * j + 1];
+          const float r[kCChunk] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int cc = 0; cc < kCChunk; ++cc) {
+            if (m & (1u << cc)) {  // warp-uniform: a real branch skips the packed products and the sums
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[cc][q] = add2(acc[cc][q], mul2(r[cc], d[q]));
+            }
+          }
+        }
+      }
+      if (ea < len) {
+#pragma unroll
+        for (int cc = 0; cc < kCChunk; ++cc) {
+          const int c = ch * kCChunk + cc;
+          if (c < C) {
+            float2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = add2(w[q], acc[cc][q]);
+            OutT* o = outp + (size_t)c * p.out_stride;
+#pragma unroll
+            for (int grp = 0; grp < 2; ++grp) {
+              const int e = grp ? eb : ea;
+              if (e + 4 <= len) {
+                Store4<OutT>::st(o + e, v[2 * grp], v[2 * grp + 1]);
+              } else {  // ragged tail: element-wise
+                const float f[4] = {v[2 * grp].x, v[2 * grp].y, v[2 * grp + 1].x, v[2 * grp + 1].y};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (e + q < len) o[e + q] = Cvt<OutT>::from_f(f[q]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename OutT>
+int launch_ring(const AggParams& base, cudaStream_t stream) {
+  AggParams p = base;
+  p.num_tiles = (p.P + kRingTile - 1) / kRingTile;
+  const int nchunks = (p.C + kCChunk - 1) / kCChunk;
+  const size_t smem = (size_t)kRingSlots * kRingTile * 4 + (size_t)nchunks * p.N * kCChunk * 4 +
+                      (size_t)((nchunks * p.N + 1) & ~1) * 4 + 2 * kRingSlots * 8;
+  auto kern = aggregate_ring_kernel<OutT>;
+  SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRingThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (int64_t)sm_count() * per_sm;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  kern<<<(unsigned)grid, kRingThreads, smem, stream>>>(p);
+  SVIT_LAUNCH_CHECK("aggregate_ring_kernel");
+  return SVIT_OK;
+}
+
 template <typename OutT>
 int dispatch_block(const AggParams& p, cudaStream_t stream) {
-  if (p.N <= 17) return launch<OutT, 128>(p, stream);  // stage = (N+1) * 4 KB
-  if (p.N <= 35) return launch<OutT, 64>(p, stream);
-  return launch<OutT, 32>(p, stream);
+  static const int mode = [] { const char* e = getenv("SVIT_AGG_RING"); return e ? atoi(e) : -1; }();  // -1 auto, 0 never, 1 always
+  // measured (scripts/microbench.py agg): the ring wins whenever staging N+1 rows per tile costs occupancy
+  if (mode == 1 || (mode < 0 && p.N > 8 && (p.C <= 8 || p.N >= 16))) return launch_ring<OutT>(p, stream);
+  if (p.N <= 17) return p.C <= 8 ? launch<OutT, 128, true>(p, stream) : launch<OutT, 128, false>(p, stream);
+  if (p.N <= 35) return launch<OutT, 64, false>(p, stream);
+  return launch<OutT, 32, false>(p, stream);
 }
 
 }  // namespace
