@@ -15,7 +15,7 @@
 // memory, and writes every coalition's row with 64/128-bit streaming stores.  The arithmetic is
 // FMUL2 (packed fp32x2 products) + FADD: three issue slots per two parameters, same rounding.
 //
-// Arithmetic: every product and every sum is a separately rounded fp32 operation
+// Arithmetic (fp32 output): every product and every sum is a separately rounded fp32 operation
 // (__fmul_rn/__fadd_rn; ptxas would otherwise contract to FMA), in ascending client order,
 // which is bit-identical to the reference whenever frozenset(coalition) iterates in ascending
 // order.  Algorithmic bytes per launch:
@@ -81,6 +81,27 @@ __device__ __forceinline__ float2 mul2(float r, float2 d) {
   return o;
 }
 __device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+// acc + r * d with ONE rounding (FFMA2): only for 16-bit outputs, see accumulate()
+__device__ __forceinline__ float2 fma2(float r, float2 d, float2 acc) {
+  float2 o;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(o.x), "=f"(o.y)
+      : "f"(r), "f"(d.x), "f"(d.y), "f"(acc.x), "f"(acc.y));
+  return o;
+}
+// fp32 outputs reproduce the reference's arithmetic exactly (product rounded, then the sum).  16-bit
+// outputs -- the operand feed of the 16-bit GEMMs, which the reference has no counterpart of -- use a
+// fused multiply-add: the result is rounded to 11 / 8 mantissa bits right afterwards, the fused
+// operation is at most one fp32 ulp away from the two-rounding value before that, and it takes a third
+// of the issue slots, which is what keeps the kernel HBM-bound at power-capped SM clocks.
+template <typename OutT>
+__device__ __forceinline__ float2 accumulate(float2 acc, float r, float2 d) {
+  if constexpr (sizeof(OutT) == 4)
+    return add2(acc, mul2(r, d));
+  else
+    return fma2(r, d, acc);
+}
 
 // 4 consecutive outputs, one streaming vector store (8 bytes for fp16/bf16, 16 for fp32)
 template <typename OutT> struct Store4;
@@ -227,7 +248,7 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
           for (int cc = 0; cc < kCChunk; ++cc) {
             if (mc & (1u << cc)) {  // warp-uniform: a real branch skips the 4 packed products and the 8 sums
 #pragma unroll
-              for (int q = 0; q < 4; ++q) acc[cc][q] = add2(acc[cc][q], mul2(r[cc], d[q]));
+              for (int q = 0; q < 4; ++q) acc[cc][q] = accumulate<OutT>(acc[cc][q], r[cc], d[q]);
             }
           }
         }
@@ -435,7 +456,7 @@ __global__ void __launch_bounds__(kRingThreads) aggregate_ring_kernel(const __gr
           for (int cc = 0; cc < kCChunk; ++cc) {
             if (m & (1u << cc)) {  // warp-uniform: a real branch skips the packed products and the sums
 #pragma unroll
-              for (int q = 0; q < 4; ++q) acc[cc][q] = add2(acc[cc][q], mul2(r[cc], d[q]));
+              for (int q = 0; q < 4; ++q) acc[cc][q] = accumulate<OutT>(acc[cc][q], r[cc], d[q]);
             }
           }
         }
