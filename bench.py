@@ -213,6 +213,8 @@ def run_ours(a):
     if ws > 1:
         import torch.distributed as td
 
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+
         td.init_process_group("nccl", rank=rank, world_size=ws, device_id=dev)
     _lib.device_info()
 

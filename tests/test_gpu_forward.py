@@ -113,6 +113,23 @@ def test_vit_base_geometry_against_reference_fixture(prec):
     assert err < LOGIT_TOL[prec]
 
 
+@pytest.mark.parametrize("prec", ["f32", "f16", "bf16"])
+def test_vit_large_geometry_against_oracle(prec):
+    """ViT-L/16 @ 224 (h = 1024, 16 heads, ff = 4096; BASELINE config 4 runs it in bf16), 2 layers,
+    3 clients: logits of three coalitions vs oracle/restate.py."""
+    cfg, w0, _, deltas, n_train, images, labels = synthetic_game("large", 224, 10, 3, 6, 7, layers=2)
+    coalitions = [(0,), (1, 2), (0, 1, 2)]
+    eng = make_engine(cfg, w0, deltas, images, labels, prec, coalition_batch=3, image_chunk=4)
+    eng.evaluate(ratio_rows(coalitions, n_train))
+    logits = eng.last_logits.cpu()
+    worst = 0.0
+    for ci, S in enumerate(coalitions):
+        want = restate.vit_forward(restate.coalition_state_dict(w0, deltas, n_train, list(S)), cfg, images)
+        worst = max(worst, (logits[ci] - want).abs().max().item())
+    print(f"[{prec}] ViT-L max |dlogit| = {worst:.3e}")
+    assert worst < LOGIT_TOL[prec]
+
+
 def test_aggregated_model_rows_bit_exact_vs_oracle():
     """K1 through the engine on the real parameter layout: W_S == oracle W_S, bit for bit."""
     from shapley_vit_b200 import layout
