@@ -264,7 +264,7 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
 // memory tile (conflict-free both ways), then position-embedding / residual adds and the global
 // stores in a COALESCED layout (a quarter-warp covers one contiguous 128-byte row segment).
 
-enum { EPI_DIRECT = 0, EPI_RESIDUAL = 1, EPI_GENERIC = 2 };  // see epilogue_chunk
+enum { EPI_DIRECT = 0, EPI_RESIDUAL = 1, EPI_GENERIC = 2, EPI_REDUCE = 3 };  // see epilogue_chunk
 
 // the residual fragment of one chunk in the coalesced layout (8 x float4 per lane), read ahead of use
 template <int MODE>
@@ -288,6 +288,8 @@ __device__ __forceinline__ void residual_prefetch(const EpiArgs& e, int g, int m
 //   EPI_DIRECT    + bias (+ GELU) -> cast -> store; no row remap           (QKV, MLP-up)
 //   EPI_RESIDUAL  + bias -> + fp32 residual -> fp32 store; no row remap    (attention out-proj, MLP-down)
 //   EPI_GENERIC   everything decided at run time                           (patch embedding, odd callers)
+//   EPI_REDUCE    + bias -> out += value by a TMA reduce-add (out IS the residual, fp32, in place): the
+//                 residual never travels through the SM; pair kernel only       (out-proj, MLP-down in the forward)
 
 //   v        the thread's 32 accumulators (row m_slab + lane, columns n .. n+31)
 //   stg      this warp's staging tile (kStagingPerWarp bytes of shared memory)
@@ -400,6 +402,43 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, int g, int m_sl
   __syncwarp();  // the staging tile is rewritten by the next chunk
 }
 
+// EPI_REDUCE: out[rows, n .. n+31] += acc + bias, as one TMA reduce-add of the staged fp32 chunk.
+// fl(x + fl(acc + bias)) is the same two roundings the reference performs (dense output, then the
+// residual add, HF modeling_vit.py:265-268 / :337); the addition happens in the L2, so the residual
+// stream is neither loaded into nor stored from the SM, and nothing in the epilogue waits on HBM.
+// `stg` alternates between two tiles per warp: the reduce issued two chunks ago must have read its
+// tile before it is rewritten (cp.async.bulk.wait_group.read 1).  Rows >= M are clipped by the map.
+__device__ __forceinline__ void epilogue_chunk_reduce(const EpiArgs& e, const CUtensorMap* map_out, int g, int m_slab, int n,
+                                                      float* v, uint8_t* stg, int lane, const float* bias_s) {
+  if (e.bias) {
+    float4 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = reinterpret_cast<const float4*>(bias_s)[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 a = fadd2(make_float2(v[4 * i], v[4 * i + 1]), make_float2(t[i].x, t[i].y));
+      const float2 b = fadd2(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(t[i].z, t[i].w));
+      v[4 * i] = a.x, v[4 * i + 1] = a.y, v[4 * i + 2] = b.x, v[4 * i + 3] = b.y;
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  __syncwarp();
+  // fp32 tile, rows of 128 bytes, 16-byte chunk j of row r at chunk (j ^ (r & 7)) = TMA SWIZZLE_128B
+  uint8_t* wbase = stg + lane * 128;
+  const int sw = lane & 7;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(wbase + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map_out),
+                 "r"(smem_u32(stg)), "r"(n), "r"(m_slab), "r"(g)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
 // ragged N (not a multiple of 8, or a partial last chunk): element-wise in the row layout
 __device__ __forceinline__ void epilogue_row_ragged(const EpiArgs& e, int g, int r, int n, const float* v) {
   const int64_t orow = epi_out_row(e, r);
@@ -418,7 +457,8 @@ __device__ __forceinline__ void epilogue_row_ragged(const EpiArgs& e, int g, int
 template <int BN, int MODE, class Arrive>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape& sh, int g, int m_slab, int n0, int half,
                                               int lane, uint32_t tmem_acc, uint8_t* stg, float* bias_s,
-                                              uint64_t* tfull, uint32_t parity, Arrive arrive) {
+                                              uint64_t* tfull, uint32_t parity, Arrive arrive,
+                                              const CUtensorMap* map_out = nullptr) {
   constexpr int NCH = BN / 64;  // 32-column chunks per warp (2 or 4)
   const bool vec_ok = (sh.N & 7) == 0;
   const int n_w = n0 + half * (BN / 2);
@@ -430,7 +470,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape&
     reinterpret_cast<float4*>(bias_s)[lane] = b;
     __syncwarp();
   }
-  const bool use_res = (MODE == EPI_RESIDUAL || (MODE == EPI_GENERIC && epi.residual)) && vec_ok && rows_ok;
+  const bool use_res = (MODE == EPI_RESIDUAL || (MODE == EPI_GENERIC && epi.residual)) && vec_ok && rows_ok;  // (EPI_REDUCE: no)
   float4 res0[8], res1[8];
   if (use_res && n_w + 32 <= sh.N) residual_prefetch<MODE>(epi, g, m_slab, n_w, lane, res0);
   mbar_wait(tfull, parity);
@@ -441,6 +481,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape&
   const uint32_t t0 = tmem_acc + (uint32_t)(half * (BN / 2));
   tmem_ld_32x32_issue(t0, v0);
   auto chunk = [&](int n, float* v, const float4 (&res)[8], int c) {
+    if (MODE == EPI_REDUCE) {
+      if (rows_ok) epilogue_chunk_reduce(epi, map_out, g, m_slab, n, v, stg + (c & 1) * kStagingPerWarp, lane, bias_s + 32 * c);
+      return;
+    }
     if (n < sh.N && rows_ok) {
       if (vec_ok && n + 32 <= sh.N)
         epilogue_chunk<MODE>(epi, g, m_slab, n, v, stg, lane, res, bias_s + 32 * c);
@@ -584,8 +628,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ---- the CTA-pair kernel (cta_group::2) ----------------------------------------------------
-template <int STAGES_>
+template <int STAGES_, int STG_PER_WARP = kStagingPerWarp>
 struct Cfg2 {
+  static constexpr int kStg = STG_PER_WARP;
   static constexpr int BN = 256;                    // N of the pair tile; each CTA stages BN / 2 rows of B
   static constexpr int STAGES = STAGES_;
   static constexpr int A_BYTES = BM * 128;          // this CTA's 128 rows of A, one 128-byte k-block
@@ -593,15 +638,20 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
-  static constexpr int STAGING_BYTES = kEpiWarps * (kStagingPerWarp + kBiasPerWarp);
+  static constexpr int STAGING_BYTES = kEpiWarps * (STG_PER_WARP + kBiasPerWarp);
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + NUM_BARS * 8 + 16 + 1024;
 };
+// the reduce mode double-buffers its staging tile (a TMA reduce reads it asynchronously) and gives up a stage for it
+template <int MODE> struct PairCfg { using type = Cfg2<5>; };
+template <> struct PairCfg<EPI_REDUCE> { using type = Cfg2<4, 2 * kStagingPerWarp>; };
 
 template <int KIND, int STAGES, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const TcShape sh, const EpiArgs epi, const uint32_t idesc) {
-  using C = Cfg2<STAGES>;
+                    const __grid_constant__ CUtensorMap tma_out, const TcShape sh, const EpiArgs epi,
+                    const uint32_t idesc) {
+  using C = typename PairCfg<MODE>::type;
+  static_assert(C::STAGES == STAGES, "stage count is a function of the epilogue mode");
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
   // identical carve-up in both CTAs: the pair MMA and the multicast commits address the peer's
@@ -696,8 +746,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   } else {  // ===== epilogue warps (both CTAs, each its own 128 rows) =====
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
-    uint8_t* stg = staging + (size_t)(warp - 2) * kStagingPerWarp;
-    float* bias_s = reinterpret_cast<float*>(staging + (size_t)kEpiWarps * kStagingPerWarp + (size_t)(warp - 2) * kBiasPerWarp);
+    uint8_t* stg = staging + (size_t)(warp - 2) * C::kStg;
+    float* bias_s = reinterpret_cast<float*>(staging + (size_t)kEpiWarps * C::kStg + (size_t)(warp - 2) * kBiasPerWarp);
     const uint32_t tempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     int acc = 0;
     uint32_t aph = 0;
@@ -708,9 +758,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const uint32_t te = tempty0 + 8u * acc;
       epilogue_tile<BN, MODE>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
                         tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), stg, bias_s, &tfull_bar[acc], aph,
-                        [te] { mbar_arrive_cluster(te); });
+                        [te] { mbar_arrive_cluster(te); }, &tma_out);
       if ((acc ^= 1) == 0) aph ^= 1;
     }
+    if (MODE == EPI_REDUCE && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all reduce-adds performed
   }
   // Nobody leaves while the peer may still multicast a commit into, or read operands from, this
   // CTA's shared memory; TMEM is released by both CTAs after that.
@@ -748,17 +799,24 @@ int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcShape sh, const Ep
   return SVIT_OK;
 }
 
-template <int KIND, int STAGES, int MODE>
+template <int KIND, int MODE>
 int launch_tc2s(const CUtensorMap& ma, const CUtensorMap& mb, TcShape sh, const EpiArgs& epi, uint32_t idesc,
                 cudaStream_t stream) {
-  using C = Cfg2<STAGES>;
+  using C = typename PairCfg<MODE>::type;
+  constexpr int STAGES = C::STAGES;
+  CUtensorMap mo = ma;  // only the reduce mode reads it
+  if (MODE == EPI_REDUCE) {
+    int rc = encode_map_3d(&mo, SVIT_F32, epi.out, (uint64_t)sh.N, (uint64_t)sh.M, (uint64_t)sh.G, (uint64_t)sh.N * 4,
+                           (uint64_t)(sh.G > 1 ? epi.out_gs : (int64_t)sh.M * sh.N) * 4, 32, 32);
+    if (rc) return rc;
+  }
   sh.tiles_m = (sh.M + 2 * BM - 1) / (2 * BM);
   sh.tiles_n = sh.N / C::BN;
   sh.total_tiles = (int64_t)sh.G * sh.tiles_m * sh.tiles_n;
   auto kern = gemm_tc2_kernel<KIND, STAGES, MODE>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   const int64_t npairs = std::min<int64_t>(sh.total_tiles, sm_count() / 2);
-  kern<<<(unsigned)(2 * npairs), kThreads, C::SMEM, stream>>>(ma, mb, sh, epi, idesc);
+  kern<<<(unsigned)(2 * npairs), kThreads, C::SMEM, stream>>>(ma, mb, mo, sh, epi, idesc);
   SVIT_LAUNCH_CHECK("gemm_tc2_kernel");
   return SVIT_OK;
 }
@@ -766,11 +824,16 @@ int launch_tc2s(const CUtensorMap& ma, const CUtensorMap& mb, TcShape sh, const 
 template <int KIND>
 int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const TcShape& sh, const EpiArgs& epi, uint32_t idesc,
                cudaStream_t stream) {
+  static const bool no_reduce = [] { const char* e = getenv("SVIT_GEMM_NO_REDUCE"); return e && e[0] == '1'; }();
   const bool remap = epi.rows_in > 0;
-  if (!epi.rowvec && !epi.residual && !remap) return launch_tc2s<KIND, 5, EPI_DIRECT>(ma, mb, sh, epi, idesc, stream);
-  if (!epi.rowvec && epi.residual && !remap && !epi.gelu && epi.out_dtype == SVIT_F32)
-    return launch_tc2s<KIND, 5, EPI_RESIDUAL>(ma, mb, sh, epi, idesc, stream);
-  return launch_tc2s<KIND, 5, EPI_GENERIC>(ma, mb, sh, epi, idesc, stream);
+  if (!epi.rowvec && !epi.residual && !remap) return launch_tc2s<KIND, EPI_DIRECT>(ma, mb, sh, epi, idesc, stream);
+  if (!epi.rowvec && epi.residual && !remap && !epi.gelu && epi.out_dtype == SVIT_F32) {
+    // in place (out IS the residual): the add can be done by the L2 (TMA reduce-add)
+    if (!no_reduce && epi.residual == epi.out && (sh.G == 1 || epi.residual_gs == epi.out_gs))
+      return launch_tc2s<KIND, EPI_REDUCE>(ma, mb, sh, epi, idesc, stream);
+    return launch_tc2s<KIND, EPI_RESIDUAL>(ma, mb, sh, epi, idesc, stream);
+  }
+  return launch_tc2s<KIND, EPI_GENERIC>(ma, mb, sh, epi, idesc, stream);
 }
 
 }  // namespace
