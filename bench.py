@@ -346,10 +346,20 @@ def run_ours(a):
     g_ms, g_flops, g_n = timing["gemm"]
     tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    # DRAM bytes per GEMM launch from the committed ncu --set full capture of this configuration
+    traffic, traffic_agg = None, None
+    if a.vit == "base" and a.coalition_batch == 8 and a.image_chunk == 128 and a.precision in ("f16", "bf16"):
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            traffic, traffic_agg = tj["gemm_avg_dram_bytes_per_launch"], tj["aggregate_dram_bytes_per_launch"]
+        except Exception:
+            pass
     roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2 grouped GEMM)" if a.precision != "f32" else "gemm_simt_kernel",
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                 "peak_source": f"{peak_src}; sustained figure (kernel timed inside a long step); burst = {peaks['bf16_tflops']}",
-                "traffic": None, "launches": int(g_n), "avg_launch_ms": g_ms / max(g_n, 1),
+                "traffic": traffic, "algorithmic_flops_per_launch": g_flops / max(g_n, 1),
+                "launches": int(g_n), "avg_launch_ms": g_ms / max(g_n, 1),
                 "share_of_step": g_ms / elapsed_ms}
     a_ms, a_flops, a_n = timing["attention"]
     l_ms, l_bytes, l_n = timing["layernorm"]
@@ -363,7 +373,7 @@ def run_ours(a):
     roofline_agg = {"bound": "hbm", "kernel": "aggregate_kernel (K1)", "achieved": agg_bytes / (agg_ms / 1e3) / 1e9 if agg_ms else None,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "launches": agg_launches,
                     "frac": (agg_bytes / (agg_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if agg_ms else None,
-                    "algorithmic_bytes_per_step": agg_bytes / a.steps}
+                    "algorithmic_bytes_per_step": agg_bytes / a.steps, "traffic": traffic_agg}
     model_flops = cfg.flops_per_image() * a.val * Cb * a.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": a.steps, "warmup": a.warmup,

@@ -5,13 +5,16 @@ TAG=${1:-r01}
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --val 1024"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.log; exit 1; }
-tail -1 gpurun_out/${TAG}_plain.log | cut -c1-400
+tail -1 gpurun_out/${TAG}_plain.log | cut -c1-300
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 30 -c 4 -o gpurun_out/${TAG}_gemm -f $CMD > gpurun_out/${TAG}_ncu_gemm.log 2>&1
+# one encoder layer's four GEMMs (QKV, out-proj, MLP-up, MLP-down): skip the patch-embedding GEMM and 7 layers
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc2_kernel -s 29 -c 4 -o gpurun_out/${TAG}_gemm -f $CMD > gpurun_out/${TAG}_ncu_gemm.log 2>&1
 echo "gemm full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:aggregate_kernel -c 4 -o gpurun_out/${TAG}_aggregate -f $CMD > gpurun_out/${TAG}_ncu_agg.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:aggregate -c 4 -o gpurun_out/${TAG}_aggregate -f $CMD > gpurun_out/${TAG}_ncu_agg.log 2>&1
 echo "aggregate full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:attention_mma_kernel -s 4 -c 2 -o gpurun_out/${TAG}_attention -f $CMD > gpurun_out/${TAG}_ncu_att.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:attention_tc_kernel -s 4 -c 1 -o gpurun_out/${TAG}_attention -f $CMD > gpurun_out/${TAG}_ncu_att.log 2>&1
 echo "attention full rc=$?"
-ls -la gpurun_out/
+ncu --set full --clock-control none --import-source on -k regex:layernorm_kernel -s 4 -c 1 -o gpurun_out/${TAG}_layernorm -f $CMD > gpurun_out/${TAG}_ncu_ln.log 2>&1
+echo "layernorm full rc=$?"
+ls -la gpurun_out/ | grep ${TAG}

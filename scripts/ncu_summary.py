@@ -26,6 +26,8 @@ KEYS = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__average_warp_latency_issue_stalled_long_scoreboard_per_warp_active.pct",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct",
 ]
 
 
