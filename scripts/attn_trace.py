@@ -14,7 +14,7 @@ ops.attention(qkv, 12); torch.cuda.synchronize()
 lib.svit_debug_attention_trace(C.c_void_p(0))
 t = buf.cpu().view(24, 16)
 t0 = int(t[0][t[0] > 0].min())
-names = ["g0 S", "g0 P", "g0 O", "g0 st", "g1 S", "g1 P", "g1 O", "g1 st", "m qk0", "m pv1", "m qk1", "m pv0", "m end", "g0 max", "g1 max"]
+names = ["g0 S", "g0 P", "g0 O", "g0 st", "g1 S", "g1 P", "g1 O", "g1 st", "m qk0", "m pv1", "m qk1", "m pv0", "m end"]
 print("item " + " ".join(f"{n:>7s}" for n in names))
 for i in range(24):
-    print(f"{i:4d} " + " ".join(f"{(int(t[i][k]) - t0) if t[i][k] > 0 else -1:7d}" for k in range(15)))
+    print(f"{i:4d} " + " ".join(f"{(int(t[i][k]) - t0) if t[i][k] > 0 else -1:7d}" for k in range(13)))
