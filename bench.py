@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=48)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-clients", type=int, default=4)
+    ap.add_argument("--parity-images", type=int, default=256)
     return ap.parse_args()
 
 
@@ -192,6 +195,61 @@ def run_reference(a):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev):
+    """The second half of the metric ("Shapley abs err"): exact Shapley of a reduced game (first
+    `--parity-clients` clients, first `--parity-images` validation images, every coalition) computed in
+    the benchmarked precision and in the library's fp32 mode (fp32 operands, CUDA-core GEMMs -- the mode
+    the GPU tests hold to the oracle at 100 % top-1 agreement and 4e-8 Shapley error), on the same
+    device buffers.  Returns max |d Shapley|, the per-coalition top-1 agreement and the utility gap."""
+    import torch
+
+    from shapley_vit_b200 import synth
+    from shapley_vit_b200.engine import CoalitionEngine
+    from shapley_vit_b200.estimators import powerset, shapley_exact
+    from shapley_vit_b200.fl import ClientBase, ServerBase
+    from shapley_vit_b200.game import Game
+
+    n_c, n_img = min(a.parity_clients, a.clients), min(a.parity_images, a.val)
+    images, labels = images_host[:n_img], labels_host[:n_img]
+    n_train = synth.client_sizes(a.clients)[:n_c]
+    coalitions = list(powerset(range(n_c)))
+    sv, preds, util = {}, {}, {}
+    t0 = time.perf_counter()
+    for prec in (a.precision, "f32"):
+        eng = CoalitionEngine(cfg, w0, deltas[:n_c].contiguous(), images, labels, precision=prec, coalition_batch=5,
+                              image_chunk=min(32, n_img), device=dev, keep_logits=True)
+        clients = [ClientBase(i, {}, None, synth.SizedStub(n)) for i, n in enumerate(n_train)]
+        server = ServerBase({}, None, clients, None, eng.val, None)
+        rows = []
+        for S in coalitions:
+            r = server.get_agg_ratio(selected_clients=[clients[j] for j in S])
+            row = [0.0] * n_c
+            for j, v in zip(S, r):
+                row[j] = v
+            rows.append(row)
+        p = []
+        for s0 in range(0, len(rows), 5):
+            eng.evaluate(rows[s0:s0 + 5])
+            p.append(eng.last_logits.argmax(dim=2).cpu())
+        preds[prec] = torch.cat(p)
+        game = Game(clients, server, None, [None] * n_c, [True] * n_c, [0.0, 0.0], 2, {"precision": prec})
+        game._engine = eng
+        phi = shapley_exact(game)
+        sv[prec] = [[phi[d][c] for c in range(n_c)] for d in range(2)]
+        util[prec] = [game.eval_utility(S) for S in coalitions]
+        del eng, game
+        torch.cuda.empty_cache()
+    ref = "f32"
+    err = max(abs(x - y) for d in range(2) for x, y in zip(sv[a.precision][d], sv[ref][d]))
+    agree = (preds[a.precision] == preds[ref]).float().mean(dim=1)
+    du = max(abs(u[0] - v[0]) for u, v in zip(util[a.precision], util[ref]))
+    return {"shapley_abs_err": err, "top1_agreement_min": float(agree.min()), "top1_agreement_mean": float(agree.mean()),
+            "accuracy_utility_abs_err_max": du, "reference": "this library's fp32 mode (held to the CPU oracle in tests/test_gpu_forward.py)",
+            "game": f"{n_c} clients, {len(coalitions)} coalitions, {n_img} images, {a.vit} @ {a.image}px, exact Shapley",
+            "seconds": time.perf_counter() - t0}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -341,6 +399,13 @@ def run_ours(a):
             td.destroy_process_group()
         return
 
+    parity = None
+    if ws == 1 and not a.no_parity and a.precision != "f32":
+        try:
+            parity = parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev)
+        except Exception as e:  # never lose the throughput line to the parity leg
+            parity = {"error": repr(e)}
+
     # ---- roofline of the dominant kernel (the tcgen05 grouped GEMM) ---------------------------
     peaks, peak_src = load_peaks()
     g_ms, g_flops, g_n = timing["gemm"]
@@ -384,7 +449,7 @@ def run_ours(a):
                    "l2": "inputs per step (2.7 GB delta stack, 3 GB patch matrix) exceed the 126 MB L2; no flush needed",
                    "model_tflops_per_s_per_gpu": model_flops / (elapsed_ms / 1e3) / 1e12},
         "roofline": roofline, "roofline_aggregate": roofline_agg, "breakdown": breakdown,
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
     }
     if ws == 1 and not a.no_cpu_baseline:
         cpu = CpuPath(a)
