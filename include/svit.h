@@ -9,6 +9,8 @@
  *   svit_aggregate        <- get_aggregated_model      federated_learning/utils.py:781-792
  *                            + ServerBase.model_agg_lazy federated_learning/server2.py:121-127
  *                            (FedAvg ratios from ServerBase.get_agg_ratio, server2.py:68-81)
+ *   svit_aggregate_onto   <- the per-round accumulation of compute_utilities_lazy
+ *                            fed_client_contribution/utils_fed_shapley.py:146-196 (model_agg_lazy over a list)
  *   svit_patchify,
  *   svit_forward_batched  <- net(img).logits inside evaluation, federated_learning/utils.py:886
  *                            (HF ViTForImageClassification built at start.py:258-267)
@@ -109,6 +111,16 @@ int svit_layout_segment(const svit_vit_cfg* cfg, int32_t index, svit_segment* ou
 int svit_aggregate(const float* deltas, int64_t delta_stride, const float* w0, const float* ratios,
                    void* out, int64_t out_stride, int out_dtype, int64_t P, int N, int C,
                    svit_stream_t stream);
+
+/* One more FL round folded onto per-coalition partial models (the reference's multi-round "lazy"
+ * reconstruction: ServerBase.model_agg_lazy with a LIST of per-round aggregates, server2.py:121-127,
+ * driven by compute_utilities_lazy, fed_client_contribution/utils_fed_shapley.py:146-196):
+ *   out[c, p] = cast( base[c, p] + sum_{j : ratios[c,j] != 0, ascending j} ratios[c,j] * deltas[j, p] )
+ * base device [C, base_stride] fp32 (may alias out when out_dtype is SVIT_F32); everything else as in
+ * svit_aggregate.  A coalition without a member in this round has an all-zero ratio row: out = base. */
+int svit_aggregate_onto(const float* deltas, int64_t delta_stride, const float* base, int64_t base_stride,
+                        const float* ratios, void* out, int64_t out_stride, int out_dtype, int64_t P, int N,
+                        int C, svit_stream_t stream);
 
 /* ---- forward ------------------------------------------------------------------------ */
 typedef struct svit_plan svit_plan; /* opaque: geometry, layout table, TMA descriptors */

@@ -16,7 +16,9 @@ so parity is pinned on outputs of the reference's own code driven here through
 * ``base_probe``  -- ViT-B/16 at 224 px geometry (T = 197, 12 heads), 3 clients,
   8 images: logits for three coalitions (pins the restated forward at the
   BASELINE config 2 geometry);
-* ``estimators``  -- every reference estimator on table-driven toy games.
+* ``estimators``  -- every reference estimator on table-driven toy games;
+* ``lazy_rounds`` -- the multi-round reconstruction ``compute_utilities_lazy``
+  (utils_fed_shapley.py:146-196) on 3 clients x 3 FL rounds with a selection matrix.
 
 RNG protocol for the stochastic estimators:
 ``np.random.RandomState(None)`` is replaced by ``RandomState(seed)``,
@@ -266,17 +268,53 @@ def golden_estimators(ref):
     print("estimators done")
 
 
+def golden_lazy(ref):
+    """compute_utilities_lazy (reference utils_fed_shapley.py:146-196) on 3 clients x 3 FL rounds with a
+    per-round selection matrix, 2-layer ViT-Ti/16 @ 32 px, 200 images."""
+    import importlib
+    import types
+
+    from torch.utils.data import DataLoader
+
+    ufs = importlib.import_module("refshapleyserver.fed_client_contribution.utils_fed_shapley")
+    cfg, w0, round_sds, selection, n_train, images, labels = synth.lazy_rounds_inputs()
+    loader = DataLoader(synth.DictSampleDataset(images, labels), batch_size=128, shuffle=False)
+    init_model = build_hf_vit(cfg, w0)
+    round_deltas = [[ref.get_difference_between_network_weights(build_hf_vit(cfg, sd), init_model) for sd in sds]
+                    for sds in round_sds]
+    args = types.SimpleNamespace(num_clients=len(n_train))
+    with ref_shim.quiet():
+        acc0, loss0 = ref.evaluation(args, init_model, loader)
+    clients = [ref.ClientBase(i, args, init_model, synth.SizedStub(n)) for i, n in enumerate(n_train)]
+    server = ref.ServerBase(args, init_model, clients, None, loader, None)
+    subsets = ref.utils_shapley.powerset(range(len(n_train)))
+    out = {"seed": 11, "n_clients": len(n_train), "n_rounds": len(selection), "n_val": int(images.shape[0]),
+           "selection": selection, "n_train": list(n_train), "previous_utility": [acc0, loss0],
+           "subsets": [list(k) for k in subsets.keys()], "cases": []}
+    for current_round, include_from in ((2, 0), (2, 1), (1, 0)):
+        with ref_shim.quiet():
+            util, _ = ufs.compute_utilities_lazy(args, [acc0, loss0], round_deltas, selection, server, clients, init_model,
+                                                 subsets, 2, current_round, include_from)
+        out["cases"].append({"current_round": current_round, "include_from_round": include_from,
+                             "acc": [float(x) for x in util[0]], "loss": [float(x) for x in util[1]]})
+    with open(os.path.join(GOLD, "lazy_rounds.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("lazy_rounds done")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = ref_shim.load()
-    which = sys.argv[1:] or ["estimators", "cfg1", "base"]
+    which = sys.argv[1:] or ["estimators", "cfg1", "base", "lazy"]
     if "estimators" in which:
         golden_estimators(ref)
     if "cfg1" in which:
         golden_cfg1(ref)
     if "base" in which:
         golden_base_probe(ref)
+    if "lazy" in which:
+        golden_lazy(ref)
 
 
 if __name__ == "__main__":

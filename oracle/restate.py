@@ -80,6 +80,39 @@ def coalition_state_dict(w0, deltas: Sequence[Dict[str, torch.Tensor]], n_train:
     return model_agg_lazy(w0, [agg] if agg is not None else [])
 
 
+def lazy_state_dict(w0, round_deltas, selection_matrix, n_train: Sequence[int], coalition: Sequence[int],
+                    current_round: int, include_from_round: int = 0):
+    """The model compute_utilities_lazy reconstructs for one subset (reference
+    fed_client_contribution/utils_fed_shapley.py:168-183): for every round t in
+    [include_from_round, current_round] the FedAvg aggregate of the members selected in that round,
+    added to W_0 in round order (model_agg_lazy, server2.py:121-127)."""
+    per_round = []
+    for t in range(current_round + 1):
+        if t < include_from_round:
+            continue
+        members = [j for j in coalition if selection_matrix[t][j]]
+        if members:
+            per_round.append(get_aggregated_model([round_deltas[t][j] for j in members],
+                                                  get_agg_ratio([n_train[j] for j in members])))
+    return model_agg_lazy(w0, per_round)
+
+
+def compute_utilities_lazy(w0, round_deltas, selection_matrix, n_train, cfg, images, labels, previous_utility,
+                           current_round: int, include_from_round: int = 0):
+    """Multi-round "lazy" utilities of every NON-EMPTY subset in powerset order.
+    Follows reference fed_client_contribution/utils_fed_shapley.py:146-196.
+    Returns (utilities [2][n_subsets], subsets)."""
+    n = len(n_train)
+    subsets = list(powerset(range(n)))
+    acc, loss = [], []
+    for S in subsets:
+        sd = lazy_state_dict(w0, round_deltas, selection_matrix, n_train, S, current_round, include_from_round)
+        a, l = evaluation(sd, cfg, images, labels)
+        acc.append(a - previous_utility[0])
+        loss.append(l - previous_utility[1])
+    return [acc, loss], subsets
+
+
 def reference_member_order(coalition: Iterable[int], selection: Sequence[bool] | None = None) -> List[int]:
     """The order in which the reference sums a coalition: iteration order of
     ``frozenset(coalition)`` filtered by the selection vector

@@ -21,7 +21,7 @@ OPERAND_DTYPE = {PREC_F32: F32, PREC_TF32: F32, PREC_BF16: BF16, PREC_F16: F16}
 
 EXPORTS = [
     "svit_version", "svit_last_error", "svit_device_info", "svit_layout_sizes", "svit_layout_segment",
-    "svit_aggregate", "svit_plan_create", "svit_plan_destroy", "svit_plan_workspace_bytes",
+    "svit_aggregate", "svit_aggregate_onto", "svit_plan_create", "svit_plan_destroy", "svit_plan_workspace_bytes",
     "svit_plan_operand_dtype", "svit_patchify", "svit_forward_batched", "svit_score", "svit_gemm",
     "svit_layernorm", "svit_attention", "svit_plan_timing_begin", "svit_plan_timing_end",
 ]
@@ -84,6 +84,7 @@ def load() -> C.CDLL:
         "svit_layout_sizes": (i32, [C.POINTER(VitCfgC), C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_int32)]),
         "svit_layout_segment": (i32, [C.POINTER(VitCfgC), C.c_int32, C.POINTER(SegmentC)]),
         "svit_aggregate": (i32, [vp, i64, vp, vp, vp, i64, i32, i64, i32, i32, vp]),
+        "svit_aggregate_onto": (i32, [vp, i64, vp, i64, vp, vp, i64, i32, i64, i32, i32, vp]),
         "svit_plan_create": (i32, [C.POINTER(VitCfgC), i32, i32, i32, C.POINTER(vp)]),
         "svit_plan_destroy": (i32, [vp]),
         "svit_plan_workspace_bytes": (i64, [vp]),

@@ -124,7 +124,9 @@ template <> struct Store4<__half> {
 struct AggParams {
   const float* deltas;
   int64_t delta_stride;
-  const float* w0;  // may be null
+  const float* w0;  // shared base row [P], may be null
+  const float* base;  // per-coalition base rows [C, base_stride] fp32 (svit_aggregate_onto), exclusive with w0
+  int64_t base_stride;
   void* out;
   int64_t out_stride;
   int64_t P;
@@ -138,12 +140,32 @@ struct AggParams {
   uint32_t masks[kMaxRatios / kCChunk];
 };
 
+
+// base[c] values of one thread's two parameter groups (per-coalition base rows of svit_aggregate_onto)
+__device__ __forceinline__ void load_base(const float* row, int ea, int eb, int len, float2 (&w)[4]) {
+  float f[8];
+#pragma unroll
+  for (int grp = 0; grp < 2; ++grp) {
+    const int e = grp ? eb : ea;
+    if (e + 4 <= len) {
+      const float4 a = *reinterpret_cast<const float4*>(row + e);
+      f[4 * grp] = a.x, f[4 * grp + 1] = a.y, f[4 * grp + 2] = a.z, f[4 * grp + 3] = a.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) f[4 * grp + q] = e + q < len ? row[e + q] : 0.f;
+    }
+  }
+  w[0] = make_float2(f[0], f[1]), w[1] = make_float2(f[2], f[3]);
+  w[2] = make_float2(f[4], f[5]), w[3] = make_float2(f[6], f[7]);
+}
+
 // dynamic smem: [STAGES][(N+1)][TILE] floats | ratio table | mask table | mbarriers [STAGES]
 // PF: issue the loads of client j + 1 before the arithmetic of client j (pays when the kernel is
 // HBM-bound, C <= 8; costs issue slots when it is instruction-bound, C > 8)
 template <typename OutT, int BLOCK, bool PF>
 __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant__ AggParams p) {
   constexpr int TILE = BLOCK * kVec;
+  constexpr int TILE_ = TILE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.N, C = p.C, S = p.stages;
   const int rows = N + 1;  // row N holds W_0
@@ -256,9 +278,12 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
         for (int cc = 0; cc < kCChunk; ++cc) {
           const int c = ch * kCChunk + cc;
           if (c < C) {
-            float2 v[4];
+            float2 v[4], wb[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = add2(w[q], acc[cc][q]);
+            for (int q = 0; q < 4; ++q) wb[q] = w[q];
+            if (p.base) load_base(p.base + (size_t)c * p.base_stride + t * TILE_, ea, eb, len, wb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = add2(wb[q], acc[cc][q]);
             OutT* o = outp + (size_t)c * p.out_stride;
 #pragma unroll
             for (int grp = 0; grp < 2; ++grp) {
@@ -339,6 +364,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // dynamic smem: [kRingSlots][kRingTile] floats | ratio table | mask table | full[kRingSlots] | empty[kRingSlots]
 template <typename OutT>
 __global__ void __launch_bounds__(kRingThreads) aggregate_ring_kernel(const __grid_constant__ AggParams p) {
+  constexpr int TILE_ = kRingTile;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.N, C = p.C;
   const int nchunks = (C + kCChunk - 1) / kCChunk;
@@ -466,9 +492,12 @@ __global__ void __launch_bounds__(kRingThreads) aggregate_ring_kernel(const __gr
         for (int cc = 0; cc < kCChunk; ++cc) {
           const int c = ch * kCChunk + cc;
           if (c < C) {
-            float2 v[4];
+            float2 v[4], wb[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = add2(w[q], acc[cc][q]);
+            for (int q = 0; q < 4; ++q) wb[q] = w[q];
+            if (p.base) load_base(p.base + (size_t)c * p.base_stride + t * TILE_, ea, eb, len, wb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = add2(wb[q], acc[cc][q]);
             OutT* o = outp + (size_t)c * p.out_stride;
 #pragma unroll
             for (int grp = 0; grp < 2; ++grp) {
@@ -521,21 +550,22 @@ int dispatch_block(const AggParams& p, cudaStream_t stream) {
 }  // namespace
 }  // namespace svit
 
-extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const float* w0, const float* ratios,
-                              void* out, int64_t out_stride, int out_dtype, int64_t P, int N, int C,
-                              svit_stream_t stream) {
-  using namespace svit;
-  SVIT_CHECK_ARG(deltas && ratios && out, "svit_aggregate: null pointer");
-  SVIT_CHECK_ARG(P >= 0 && N >= 1 && N <= 64 && C >= 1 && C <= 256, "svit_aggregate: P=%lld N=%d C=%d out of range",
-                 (long long)P, N, C);
-  SVIT_CHECK_ARG(out_dtype == SVIT_F32 || out_dtype == SVIT_BF16 || out_dtype == SVIT_F16,
-                 "svit_aggregate: unknown out_dtype %d", out_dtype);
+namespace svit {
+namespace {
+
+int aggregate_impl(const char* who, const float* deltas, int64_t delta_stride, const float* w0, const float* base,
+                   int64_t base_stride, const float* ratios, void* out, int64_t out_stride, int out_dtype, int64_t P, int N,
+                   int C, svit_stream_t stream) {
+  SVIT_CHECK_ARG(deltas && ratios && out, "%s: null pointer", who);
+  SVIT_CHECK_ARG(P >= 0 && N >= 1 && N <= 64 && C >= 1 && C <= 256, "%s: P=%lld N=%d C=%d out of range", who, (long long)P, N,
+                 C);
+  SVIT_CHECK_ARG(out_dtype == SVIT_F32 || out_dtype == SVIT_BF16 || out_dtype == SVIT_F16, "%s: unknown out_dtype %d", who,
+                 out_dtype);
   if (P == 0) return SVIT_OK;
   const int64_t p8 = round_up(P, 8);
-  if (!aligned16(deltas) || !aligned16(out) || (w0 && !aligned16(w0)) || delta_stride % 8 || out_stride % 8 ||
-      delta_stride < p8 || out_stride < p8)
-    SVIT_FAIL(SVIT_ERR_ALIGN,
-              "svit_aggregate: pointers must be 16-byte aligned and strides multiples of 8 and >= round_up(P, 8)");
+  if (!aligned16(deltas) || !aligned16(out) || (w0 && !aligned16(w0)) || (base && !aligned16(base)) || delta_stride % 8 ||
+      out_stride % 8 || delta_stride < p8 || out_stride < p8 || (base && (base_stride % 8 || base_stride < p8)))
+    SVIT_FAIL(SVIT_ERR_ALIGN, "%s: pointers must be 16-byte aligned and strides multiples of 8 and >= round_up(P, 8)", who);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int es = dtype_size(out_dtype);
   // the ratio rows travel as kernel parameters: at most kMaxRatios floats per launch
@@ -546,6 +576,8 @@ extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const f
     p.deltas = deltas;
     p.delta_stride = delta_stride;
     p.w0 = w0;
+    p.base = base ? base + (size_t)c0 * base_stride : nullptr;
+    p.base_stride = base_stride;
     p.out = static_cast<char*>(out) + (size_t)c0 * out_stride * es;
     p.out_stride = out_stride;
     p.P = P;
@@ -567,4 +599,23 @@ extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const f
     if (rc) return rc;
   }
   return SVIT_OK;
+}
+
+}  // namespace
+}  // namespace svit
+
+extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const float* w0, const float* ratios,
+                              void* out, int64_t out_stride, int out_dtype, int64_t P, int N, int C,
+                              svit_stream_t stream) {
+  return svit::aggregate_impl("svit_aggregate", deltas, delta_stride, w0, nullptr, 0, ratios, out, out_stride, out_dtype, P, N,
+                              C, stream);
+}
+
+extern "C" int svit_aggregate_onto(const float* deltas, int64_t delta_stride, const float* base, int64_t base_stride,
+                                   const float* ratios, void* out, int64_t out_stride, int out_dtype, int64_t P, int N,
+                                   int C, svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(base != nullptr, "svit_aggregate_onto: base is null");
+  return aggregate_impl("svit_aggregate_onto", deltas, delta_stride, nullptr, base, base_stride, ratios, out, out_stride,
+                        out_dtype, P, N, C, stream);
 }

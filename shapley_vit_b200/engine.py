@@ -99,6 +99,8 @@ class CoalitionEngine:
         self.kernel_launches = 0
         self.profile = False                      # bench.py: CUDA-event pairs around the K1 launches
         self.agg_spans: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+        self.round_deltas: List[torch.Tensor] = []   # multi-round mode (set_round_deltas)
+        self._partial: Optional[torch.Tensor] = None
         with torch.cuda.device(self.device):
             self.plan = ops.Plan(cfg, self.precision, self.coalition_batch, self.image_chunk, self.device)
             total = self.lay.total
@@ -171,6 +173,86 @@ class CoalitionEngine:
         if self.keep_logits:
             self.last_logits = logits.clone()
         return correct, loss
+
+    # ------------------------------------------------------------------ #
+    # multi-round "lazy" reconstruction (reference utils_fed_shapley.py:146-196 + server2.py:121-127):
+    #   W_S = W_0 + agg_{S, t0} + agg_{S, t1} + ...   one FedAvg aggregate per FL round, added in round order
+    def set_round_deltas(self, round_deltas) -> None:
+        """``round_deltas[t]``: the clients' deltas of FL round t -- a packed fp32 tensor [N, total] or a list of N
+        state-dict-like deltas (None = client absent in that round: a zero row, never selected)."""
+        packed = []
+        with torch.cuda.device(self.device):
+            for rd in round_deltas:
+                if isinstance(rd, torch.Tensor):
+                    if rd.shape != (self.n_clients, self.lay.total) or rd.dtype != torch.float32:
+                        raise ValueError(f"packed round deltas must be fp32 [N, {self.lay.total}]")
+                    packed.append(rd.to(self.device).contiguous())
+                else:
+                    host = torch.zeros((self.n_clients, self.lay.total), dtype=torch.float32)
+                    for j, d in enumerate(rd):
+                        if d is not None:
+                            pack_state_dict(self.lay, d, out=host[j])
+                    packed.append(host.to(self.device))
+        self.round_deltas = packed
+        self._partial = None
+
+    def _run_batch_rounds(self, rows_per_round: Sequence[Sequence[Sequence[float]]]):
+        """One batch of coalitions; ``rows_per_round[t][c]`` = dense FedAvg ratio row of coalition c in round t
+        (all zeros when none of its members was selected in that round)."""
+        R, Cn = len(rows_per_round), len(rows_per_round[0])
+        if R != len(self.round_deltas) or R == 0:
+            raise ValueError("one ratio table per round expected (set_round_deltas first)")
+        lay, cfg = self.lay, self.cfg
+        V, Mz = lay.vec_size, lay.mat_size
+        if self._partial is None:   # fp32 partial models [coalition_batch, total], W_0 + the rounds so far
+            self._partial = torch.empty((self.coalition_batch, lay.total), dtype=torch.float32, device=self.device)
+        part = self._partial[:Cn]
+        if self.w0 is not None:
+            part.copy_(self.w0.unsqueeze(0).expand(Cn, -1))
+        else:
+            part.zero_()
+        for t in range(R):
+            ratios = torch.as_tensor(rows_per_round[t], dtype=torch.float64).to(torch.float32)
+            D = self.round_deltas[t]
+            if t < R - 1:
+                ops.aggregate_onto(D, part, ratios, part)                       # fp32, in place, two-rounding exact
+            else:                                                                # last round: straight into the plan buffers
+                ops.aggregate_onto(D[:, :V], part[:, :V], ratios, self.wvec[:Cn], P=V)
+                ops.aggregate_onto(D[:, V:], part[:, V:], ratios, self.wmat[:Cn], P=Mz)
+        logits = self.logits[:Cn]
+        npch = cfg.n_patches
+        for s in range(0, self.n_val, self.image_chunk):
+            b = min(self.image_chunk, self.n_val - s)
+            self.plan.forward(self.wvec[:Cn], self.wmat[:Cn], self.patches[s * npch:(s + b) * npch], b, logits,
+                              image_offset=s)
+        correct, loss = ops.score(logits, self.labels)
+        if self.keep_logits:
+            self.last_logits = logits.clone()
+        return correct, loss
+
+    def evaluate_rounds(self, rows_per_round: Sequence[Sequence[Sequence[float]]]) -> Tuple[List[int], List[float]]:
+        """Like ``evaluate`` for models reconstructed from several FL rounds: ``rows_per_round[t][c]``."""
+        n = len(rows_per_round[0])
+        correct: List[int] = []
+        loss: List[float] = []
+        with torch.cuda.device(self.device):
+            pending = []
+            for s in range(0, n, self.coalition_batch):
+                pending.append(self._run_batch_rounds([rt[s:s + self.coalition_batch] for rt in rows_per_round]))
+            for c, l in pending:
+                correct += c.cpu().tolist()
+                loss += l.cpu().tolist()
+        return correct, loss
+
+    def aggregated_rows_rounds(self, rows_per_round) -> torch.Tensor:
+        """Reconstructed multi-round models (plan layout, [C, total] fp32) for parity checks."""
+        with torch.cuda.device(self.device):
+            Cn = len(rows_per_round[0])
+            part = (self.w0.unsqueeze(0).expand(Cn, -1).clone() if self.w0 is not None
+                    else torch.zeros((Cn, self.lay.total), dtype=torch.float32, device=self.device))
+            for t, rows in enumerate(rows_per_round):
+                ops.aggregate_onto(self.round_deltas[t], part, torch.as_tensor(rows, dtype=torch.float64).to(torch.float32), part)
+            return part
 
     def ratio_row(self, members: Sequence[int], ratios: Sequence[float]) -> List[float]:
         row = [0.0] * self.n_clients

@@ -60,6 +60,27 @@ def aggregate(deltas: torch.Tensor, w0: Optional[torch.Tensor], ratios: torch.Te
     return out
 
 
+def aggregate_onto(deltas: torch.Tensor, base: torch.Tensor, ratios: torch.Tensor, out: torch.Tensor,
+                   P: Optional[int] = None) -> torch.Tensor:
+    """One more FL round folded onto per-coalition partial models (svit_aggregate_onto):
+    out[c, :P] = cast(base[c, :P] + sum_j ratios[c, j] * deltas[j]).  base [C, stride] fp32 (may be ``out``
+    itself when ``out`` is fp32), ratios [C, N] on the host."""
+    _cuda(deltas, "deltas", torch.float32)
+    _cuda(base, "base", torch.float32)
+    _cuda(out, "out")
+    ratios = ratios.detach().to("cpu", torch.float32).contiguous()
+    N, width = deltas.shape
+    P = width if P is None else int(P)
+    Cn = ratios.shape[0]
+    if ratios.shape != (Cn, N) or base.shape[0] != Cn or out.shape[0] != Cn:
+        raise ValueError("ratios must be [C, N]; base and out must have C rows")
+    if deltas.stride(1) != 1 or base.stride(1) != 1 or out.stride(1) != 1:
+        raise ValueError("deltas / base / out must have unit inner stride")
+    check(_lib.load().svit_aggregate_onto(_ptr(deltas), deltas.stride(0), _ptr(base), base.stride(0), _ptr(ratios), _ptr(out),
+                                          out.stride(0), SVIT_DTYPE[out.dtype], P, N, Cn, _stream(deltas)))
+    return out
+
+
 def score(logits: torch.Tensor, labels: torch.Tensor, correct: Optional[torch.Tensor] = None,
           loss_sum: Optional[torch.Tensor] = None, accumulate: bool = False, want_pred: bool = False):
     """K5.  logits [C, n, n_cls] fp32, labels [n] int64 -> (correct int64 [C], loss_sum fp64 [C][, pred int32 [C, n]])."""

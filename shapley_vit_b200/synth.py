@@ -77,3 +77,17 @@ class SizedStub:
 
     def __len__(self) -> int:
         return self._n
+
+
+def lazy_rounds_inputs(seed: int = 11, n_clients: int = 3, n_rounds: int = 3, n_val: int = 200):
+    """Seeded inputs of the multi-round ("lazy") fixture tests/golden/lazy_rounds.json:
+    (cfg, w0, round_sds[t][j], selection[t][j], n_train, images, labels)."""
+    from . import layout
+
+    cfg = layout.vit_preset("tiny", image=32, n_cls=10, layers=2)
+    w0 = make_state_dict(cfg, seed)
+    round_sds = [[make_client_state_dict(w0, j, seed + 100 * (t + 1)) for j in range(n_clients)]
+                 for t in range(n_rounds)]
+    selection = [[True, True, False], [True, False, True], [False, True, True]][:n_rounds]
+    images, labels = make_val_set(cfg, n_val, seed)
+    return cfg, w0, round_sds, selection, client_sizes(n_clients), images, labels
