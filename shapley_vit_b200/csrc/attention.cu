@@ -121,7 +121,122 @@ int dispatch_d(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, int
   }
 }
 
+
+// ---- [CLS]-query attention: the last encoder layer ---------------------------------------------
+// The classifier reads only the [CLS] token (HF modeling_vit.py:641-642), so in the LAST layer only
+// the [CLS] query row has to attend (keys and values still come from every token).  One warp per
+// (sequence, head): lanes split the keys for the scores and the softmax, then split the channels
+// for P V.  ctx_cls is compact: [n_seq, h].  All arithmetic fp32; operands fp32 / bf16 / fp16.
+// dot product of a key row (D elements of T, 16-byte aligned) with q (fp32, shared memory), 16-byte loads
+template <typename T, int D>
+__device__ __forceinline__ float dot_row(const T* __restrict__ row, const float* __restrict__ q) {
+  constexpr int EPV = 16 / sizeof(T);  // elements per 16-byte load
+  float acc = 0.f;
+#pragma unroll
+  for (int v = 0; v < D / EPV; ++v) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(row) + v);
+    const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+    for (int i = 0; i < EPV; ++i) acc = fmaf(q[v * EPV + i], Cvt<T>::to_f(e[i]), acc);
+  }
+  return acc;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(256) attention_cls_kernel(const T* __restrict__ qkv, T* __restrict__ ctx_cls, int Tn,
+                                                            int heads, int64_t n_items) {
+  __shared__ __align__(16) float q_s[8][D];
+  __shared__ float p_s[8][256];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = blockIdx.x * 8LL + w;
+  if (item >= n_items) return;
+  const int64_t seq = item / heads;
+  const int head = (int)(item % heads);
+  const int h = heads * D;
+  const T* base = qkv + seq * (int64_t)Tn * 3 * h + head * D;
+  for (int d = lane; d < D; d += 32) q_s[w][d] = Cvt<T>::to_f(base[d]);
+  __syncwarp();
+  constexpr int KPL = 8;  // keys per lane: T <= 256
+  float s[KPL];
+  const float scale = rsqrtf((float)D);
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KPL; ++k) {  // every lane reads whole 128-byte key rows (full sectors)
+    const int j = lane + k * 32;
+    s[k] = -INFINITY;
+    if (j < Tn) {
+      s[k] = dot_row<T, D>(base + (size_t)j * 3 * h + h, q_s[w]) * scale;
+      m = fmaxf(m, s[k]);
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KPL; ++k) {
+    const int j = lane + k * 32;
+    s[k] = j < Tn ? expf(s[k] - m) : 0.f;
+    sum += s[k];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int k = 0; k < KPL; ++k) p_s[w][lane + k * 32] = s[k] * inv;
+  __syncwarp();
+  // P V: the lane owns D / 32 CONSECUTIVE channels, so a warp reads each value row as one contiguous segment
+  constexpr int CPL = D / 32;
+  float o[CPL];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) o[c] = 0.f;
+  const T* vbase = base + 2 * h + lane * CPL;
+#pragma unroll 4
+  for (int j = 0; j < Tn; ++j) {
+    const float pj = p_s[w][j];
+    T v[CPL];
+    if constexpr (CPL * sizeof(T) == 4) {
+      *reinterpret_cast<uint32_t*>(v) = __ldg(reinterpret_cast<const uint32_t*>(vbase + (size_t)j * 3 * h));
+    } else if constexpr (CPL * sizeof(T) == 8) {
+      *reinterpret_cast<uint2*>(v) = __ldg(reinterpret_cast<const uint2*>(vbase + (size_t)j * 3 * h));
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) v[c] = vbase[(size_t)j * 3 * h + c];
+    }
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) o[c] = fmaf(pj, Cvt<T>::to_f(v[c]), o[c]);
+  }
+  T* out = ctx_cls + seq * (int64_t)h + head * D + lane * CPL;
+#pragma unroll
+  for (int c = 0; c < CPL; ++c) out[c] = Cvt<T>::from_f(o[c]);
+}
+
+template <typename T>
+int launch_cls(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, int head_dim, cudaStream_t stream) {
+  const int64_t items = n_seq * heads;
+  const unsigned grid = (unsigned)((items + 7) / 8);
+  switch (head_dim) {
+    case 32: attention_cls_kernel<T, 32><<<grid, 256, 0, stream>>>((const T*)qkv, (T*)ctx, Tn, heads, items); break;
+    case 64: attention_cls_kernel<T, 64><<<grid, 256, 0, stream>>>((const T*)qkv, (T*)ctx, Tn, heads, items); break;
+    case 96: attention_cls_kernel<T, 96><<<grid, 256, 0, stream>>>((const T*)qkv, (T*)ctx, Tn, heads, items); break;
+    case 128: attention_cls_kernel<T, 128><<<grid, 256, 0, stream>>>((const T*)qkv, (T*)ctx, Tn, heads, items); break;
+    default: SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "attention: head_dim %d not supported (32/64/96/128)", head_dim);
+  }
+  SVIT_LAUNCH_CHECK("attention_cls_kernel");
+  return SVIT_OK;
+}
+
 }  // namespace
+
+// qkv [n_seq, T, 3h] -> ctx_cls [n_seq, h]: attention output of the [CLS] query (token 0) only
+int attention_cls(const void* qkv, void* ctx_cls, int dtype, int64_t n_seq, int Tn, int heads, int head_dim,
+                  cudaStream_t stream) {
+  if (n_seq == 0) return SVIT_OK;
+  SVIT_CHECK_ARG(Tn >= 1 && Tn <= 256, "attention: T=%d out of range (1..256)", Tn);
+  switch (dtype) {
+    case SVIT_F32: return launch_cls<float>(qkv, ctx_cls, n_seq, Tn, heads, head_dim, stream);
+    case SVIT_BF16: return launch_cls<__nv_bfloat16>(qkv, ctx_cls, n_seq, Tn, heads, head_dim, stream);
+    case SVIT_F16: return launch_cls<__half>(qkv, ctx_cls, n_seq, Tn, heads, head_dim, stream);
+    default: SVIT_FAIL(SVIT_ERR_ARG, "attention: bad dtype %d", dtype);
+  }
+}
 
 int attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, int heads, int head_dim,
               cudaStream_t stream) {

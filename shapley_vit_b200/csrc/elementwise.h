@@ -17,6 +17,8 @@ int head(const float* X, int64_t x_gs, const float* wvec, int64_t vec_stride, in
          float eps, cudaStream_t stream);
 int attention_mma(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, cudaStream_t stream);
 int attention_tc(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, cudaStream_t stream);
+int attention_cls(const void* qkv, void* ctx_cls, int dtype, int64_t n_seq, int T, int heads, int head_dim,
+                  cudaStream_t stream);
 int attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, int head_dim,
               cudaStream_t stream);
 

@@ -32,6 +32,7 @@ struct svit_plan {
   int max_c = 0, max_b = 0;
   int T = 0, np = 0, pd = 0;
   bool force_simt = false;
+  bool full_last_layer = false;  // SVIT_FULL_LAST_LAYER=1: compute every token of the last layer (A/B and tests)
   // workspace byte offsets for (max_c, max_b)
   size_t off_x = 0, off_xn = 0, off_qkv = 0, off_ctx = 0, off_h = 0, ws_bytes = 0;
   // optional per-kernel-class device timing (svit_plan_timing_begin / _end)
@@ -127,6 +128,8 @@ extern "C" int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_
   p->pd = cfg->channels * cfg->patch * cfg->patch;
   const char* env = getenv("SVIT_FORCE_SIMT_GEMM");  // debugging aid: CUDA-core GEMMs on 16-bit operands
   p->force_simt = env && env[0] == '1';
+  const char* fl = getenv("SVIT_FULL_LAST_LAYER");
+  p->full_last_layer = fl && fl[0] == '1';
   const size_t rows = (size_t)max_coalitions * max_images * p->T;
   const size_t es = (size_t)dtype_size(odt);
   size_t off = 0;
@@ -227,6 +230,52 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       e.bias_gs = vec_stride;
       EpiArgs ea = make_epi(&e, QKV, (int64_t)M * 3 * h, odt, M, 3 * h);
       if ((rc = gemm_dispatch(plan, Xn, xgs, mat(SVIT_SEG_WQ, l), mat_stride, C, M, 3 * h, h, ea, stream))) return rc;
+    }
+    if (l == cfg.layers - 1 && !plan->full_last_layer) {
+      // Last layer: the classifier reads only the [CLS] token (HF modeling_vit.py:641-642), so past
+      // K and V only the [CLS] rows are computed: attention of the [CLS] query, then out-proj, LN,
+      // MLP on B rows per coalition instead of B * T.  Same operations on those rows, same logits.
+      const int64_t cgs = (int64_t)B * h;  // compact [C, B, h] buffers live at the front of CTX / Xn / H
+      {
+        Timed t(plan, stream, SVIT_CLS_ATTENTION, 4.0 * C * B * (double)T * h);
+        if ((rc = attention_cls(QKV, CTX, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream))) return rc;
+      }
+      auto cls_rows = [&](svit_epilogue& e) { e.rows_in = 1, e.rows_out = T, e.row_shift = 0; };  // row b -> X row b * T
+      {
+        svit_epilogue e{};
+        e.bias = vec(SVIT_SEG_BO, l);
+        e.bias_gs = vec_stride;
+        e.residual = X;
+        e.residual_gs = xgs;
+        cls_rows(e);
+        EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, B, h);
+        if ((rc = gemm_dispatch(plan, CTX, cgs, mat(SVIT_SEG_WO, l), mat_stride, C, B, h, h, ea, stream))) return rc;
+      }
+      {
+        Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * B * h * (4.0 + es));
+        if ((rc = layernorm(X, xgs, (int64_t)T * h, vec(SVIT_SEG_LN2_G, l), vec(SVIT_SEG_LN2_B, l), vec_stride, Xn, cgs, h, odt,
+                            C, B, h, cfg.ln_eps, stream)))
+          return rc;
+      }
+      {
+        svit_epilogue e{};
+        e.bias = vec(SVIT_SEG_B1, l);
+        e.bias_gs = vec_stride;
+        e.gelu = 1;
+        EpiArgs ea = make_epi(&e, H, (int64_t)B * ff, odt, B, ff);
+        if ((rc = gemm_dispatch(plan, Xn, cgs, mat(SVIT_SEG_W1, l), mat_stride, C, B, ff, h, ea, stream))) return rc;
+      }
+      {
+        svit_epilogue e{};
+        e.bias = vec(SVIT_SEG_B2, l);
+        e.bias_gs = vec_stride;
+        e.residual = X;
+        e.residual_gs = xgs;
+        cls_rows(e);
+        EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, B, h);
+        if ((rc = gemm_dispatch(plan, H, (int64_t)B * ff, mat(SVIT_SEG_W2, l), mat_stride, C, B, h, ff, ea, stream))) return rc;
+      }
+      continue;
     }
     {
       Timed t(plan, stream, SVIT_CLS_ATTENTION, 4.0 * C * B * (double)T * T * h);
