@@ -271,7 +271,10 @@ def run_ours(a):
     if ws > 1:
         import torch.distributed as td
 
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION printf()s "NCCL version ..." to stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
         td.init_process_group("nccl", rank=rank, world_size=ws, device_id=dev)
     _lib.device_info()
