@@ -209,7 +209,6 @@ struct TcShape {
   int tiles_m, tiles_n, num_kb;
   int64_t total_tiles;
   int a_grouped;  // 0: A shared by all groups
-  int flags;      // tuning experiments (SVIT_GEMM_FLAGS)
 };
 
 // ---- packed fp32x2 arithmetic (FFMA2: two IEEE fp32 FMAs per issue slot on sm_100) ------------
@@ -865,8 +864,6 @@ int gemm_tc(int precision, const void* A, int64_t a_gs, const void* B, int64_t b
   const int bk = 128 / es;
   sh.num_kb = (K + bk - 1) / bk;
   sh.a_grouped = a_gs ? 1 : 0;
-  static const int flags = [] { const char* e = getenv("SVIT_GEMM_FLAGS"); return e ? atoi(e) : 0; }();
-  sh.flags = flags;
   SVIT_CHECK_ARG(b_gs != 0 || G == 1, "gemm_tc: B must be grouped when G > 1");
   // instruction descriptor: D fp32, A/B format, both K-major, N, M
   const uint32_t fmt = precision == SVIT_PREC_TF32 ? 2u : precision == SVIT_PREC_BF16 ? 1u : 0u;
