@@ -62,7 +62,11 @@ enum svit_precision {
   SVIT_PREC_F32 = 0,  /* fp32 operands, CUDA-core FMA GEMMs: the exact mode (small cases) */
   SVIT_PREC_TF32 = 1, /* fp32 storage, tcgen05 kind::tf32 */
   SVIT_PREC_BF16 = 2, /* bf16 operands, tcgen05 kind::f16 */
-  SVIT_PREC_F16 = 3   /* fp16 operands, tcgen05 kind::f16 (same rate as bf16, 3 more mantissa bits) */
+  SVIT_PREC_F16 = 3,  /* fp16 operands, tcgen05 kind::f16 (same rate as bf16, 3 more mantissa bits) */
+  SVIT_PREC_F16X3 = 4 /* fp32 storage; every GEMM operand is split into fp16 hi + lo halves and the product is
+                         three tcgen05 kind::f16 passes (hi*hi + hi*lo + lo*hi) into one fp32 accumulator:
+                         ~21 significant bits at a third of the f16 rate -- the tensor-core mode that meets
+                         the 99.9 % top-1 gate on random-init weights */
 };
 
 typedef struct svit_vit_cfg {
@@ -183,9 +187,16 @@ typedef struct svit_epilogue {
 /* For g < G: out[g] = epilogue( A[g] (M x K, row-major) * B[g]^T (B[g] is N x K, row-major) ).
  * A, B in the operand dtype of `precision`; out_dtype is SVIT_F32 or that operand dtype.
  * Group strides may be 0 (operand shared by all groups).  M_out = M unless rows_in > 0. */
+/* SVIT_PREC_F16X3: A and B are PRE-SPLIT fp16 matrices [rows, 2K] = [hi | lo] per row (svit_split_f16),
+ * strides in fp16 elements of that layout; K is the logical K and must be a multiple of 64. */
 int svit_gemm(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, void* out,
               int64_t out_gs, int out_dtype, int G, int M, int N, int K, const svit_epilogue* epi,
               svit_stream_t stream);
+
+/* out[g][r][0:K] = fp16(in[g][r][:]), out[g][r][K:2K] = fp16(in - hi): the operand format of
+ * SVIT_PREC_F16X3.  in: fp32 [G][rows][K] with group stride in_gs (0 = one group); out: fp16
+ * [G][rows][2K] contiguous.  K % 8 == 0; 16-byte aligned pointers. */
+int svit_split_f16(const float* in, int64_t in_gs, void* out, int G, int64_t rows, int K, svit_stream_t stream);
 
 /* y[g, r, :] = LayerNorm(x[g, r, :]) * gamma[g] + beta[g]; x fp32 [G, rows, h] (row stride x_ld),
  * y in out_dtype, biased variance, eps as given (HF ViT: 1e-12). */
@@ -197,6 +208,9 @@ int svit_layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamm
  * ctx [n_seq, T, h] = softmax(q k^T / sqrt(d)) v per head, fp32 softmax. */
 int svit_attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, int head_dim,
                    svit_stream_t stream);
+/* The attention of SVIT_PREC_F16X3: fp32 qkv / ctx, head_dim 64, every product as fp16 hi*hi + hi*lo + lo*hi
+ * on the tensor cores with fp32 accumulation and an fp32 softmax. */
+int svit_attention_f16x3(const float* qkv, float* ctx, int64_t n_seq, int T, int heads, svit_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -100,8 +100,8 @@ def bench_agg():
         del deltas, w0, out
 
 
-def bench_attn(C=8, B=128, T=197, h=768, heads=12):
-    for dt in (torch.float16, torch.bfloat16):
+def bench_attn(C=8, B=128, T=197, h=768, heads=12, dts=(torch.float16, torch.bfloat16)):
+    for dt in dts:
         qkv = (torch.randn(C * B, T, 3 * h, device="cuda") * 0.5).to(dt)
         ms = timeit(lambda: ops.attention(qkv, heads))
         fl = 4.0 * C * B * T * T * h
@@ -130,5 +130,10 @@ if __name__ == "__main__":
         bench_agg()
     if "attn" in what:
         bench_attn()
+    if "attn32" in what:   # the register-tiled fp32 kernel of the f32 / tf32 modes, the split-precision one of f16x3
+        bench_attn(C=2, dts=(torch.float32,))
+        qkv = torch.randn(1024, 197, 2304, device="cuda") * 0.5
+        ms = timeit(lambda: ops.attention_f16x3(qkv, 12))
+        print(f"attention f16x3 n_seq=1024 T=197: {ms*1e3:8.1f} us  {4.0*1024*197*197*768/ms/1e9:7.1f} TFLOP/s", flush=True)
     if "ln" in what:
         bench_ln()

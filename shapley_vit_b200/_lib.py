@@ -14,16 +14,16 @@ from . import build as _build
 
 # enums (mirror include/svit.h)
 F32, BF16, F16 = 0, 1, 2
-PREC_F32, PREC_TF32, PREC_BF16, PREC_F16 = 0, 1, 2, 3
+PREC_F32, PREC_TF32, PREC_BF16, PREC_F16, PREC_F16X3 = 0, 1, 2, 3, 4
 PRECISIONS = {"f32": PREC_F32, "fp32": PREC_F32, "tf32": PREC_TF32, "bf16": PREC_BF16, "f16": PREC_F16,
-              "fp16": PREC_F16}
-OPERAND_DTYPE = {PREC_F32: F32, PREC_TF32: F32, PREC_BF16: BF16, PREC_F16: F16}
+              "fp16": PREC_F16, "f16x3": PREC_F16X3}
+OPERAND_DTYPE = {PREC_F32: F32, PREC_TF32: F32, PREC_BF16: BF16, PREC_F16: F16, PREC_F16X3: F32}
 
 EXPORTS = [
     "svit_version", "svit_last_error", "svit_device_info", "svit_layout_sizes", "svit_layout_segment",
     "svit_aggregate", "svit_aggregate_onto", "svit_plan_create", "svit_plan_destroy", "svit_plan_workspace_bytes",
-    "svit_plan_operand_dtype", "svit_patchify", "svit_forward_batched", "svit_score", "svit_gemm",
-    "svit_layernorm", "svit_attention", "svit_plan_timing_begin", "svit_plan_timing_end",
+    "svit_plan_operand_dtype", "svit_patchify", "svit_forward_batched", "svit_score", "svit_gemm", "svit_split_f16",
+    "svit_layernorm", "svit_attention", "svit_attention_f16x3", "svit_plan_timing_begin", "svit_plan_timing_end",
 ]
 KERNEL_CLASSES = ("gemm", "attention", "layernorm", "forward")
 
@@ -66,8 +66,13 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
-    if not _build.is_current():
+    path = os.environ.get("SVIT_LIB")  # A/B runs against another build of the same ABI
+    if path:
+        if not os.path.exists(path):
+            raise RuntimeError(f"SVIT_LIB={path} does not exist")
+    else:
+        path = _build.LIB
+    if path == _build.LIB and not _build.is_current():
         try:
             _build.build()
         except Exception as e:  # a stale-but-present .so on a box without nvcc is still usable
@@ -93,8 +98,10 @@ def load() -> C.CDLL:
         "svit_forward_batched": (i32, [vp, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp, C.c_size_t, vp]),
         "svit_score": (i32, [vp, i64, vp, i32, i64, i32, vp, vp, vp, i64, i32, vp]),
         "svit_gemm": (i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, C.POINTER(EpilogueC), vp]),
+        "svit_split_f16": (i32, [vp, i64, vp, i32, i64, i32, vp]),
         "svit_layernorm": (i32, [vp, i64, i64, vp, vp, i64, vp, i64, i64, i32, i32, i64, i32, f32, vp]),
         "svit_attention": (i32, [vp, vp, i32, i64, i32, i32, i32, vp]),
+        "svit_attention_f16x3": (i32, [vp, vp, i64, i32, i32, vp]),
         "svit_plan_timing_begin": (i32, [vp]),
         "svit_plan_timing_end": (i32, [vp, C.POINTER(TimingC)]),
     }

@@ -110,8 +110,181 @@ int launch_att(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, cud
   return SVIT_OK;
 }
 
+// ---- register-tiled fp32 kernel for head_dim 64 ---------------------------------------------------
+// Same arithmetic as attention_kernel (one fp32 accumulator per score, keys and channels summed in
+// index order, expf, p = e * (1 / sum)), so the results are bit-identical to it -- but a warp owns
+// EIGHT query rows at a time: every K element read from shared memory feeds 8 FMAs and every V
+// element 4, which lifts the kernel from the shared-memory load rate (one load per FMA, 10 TFLOP/s)
+// to the FMA rate.  This is the attention of the fp32-storage precisions (f32, tf32, f16x3).
+// Shared memory: Ks [TP][68] | Vs [TP][64] | per warp q [8][64] and p [8][TP + 4]; TP = 32 * KPL.
+constexpr int kRtRows = 8;
+
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p) {
+  return make_float4(Cvt<T>::to_f(p[0]), Cvt<T>::to_f(p[1]), Cvt<T>::to_f(p[2]), Cvt<T>::to_f(p[3]));
+}
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, float4 v) {
+  p[0] = Cvt<T>::from_f(v.x), p[1] = Cvt<T>::from_f(v.y), p[2] = Cvt<T>::from_f(v.z), p[3] = Cvt<T>::from_f(v.w);
+}
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+
+template <typename T, int KPL>
+__global__ void __launch_bounds__(kAttWarps * 32) attention_rt_kernel(const T* __restrict__ qkv, T* __restrict__ ctx,
+                                                                      int Tn, int heads) {
+  constexpr int D = 64, KS = D + 4, TP = KPL * 32, PS = TP + 4;
+  extern __shared__ __align__(16) float att_smem[];
+  float* Ks = att_smem;
+  float* Vs = Ks + TP * KS;
+  float* Qs = Vs + TP * D;
+  float* Ps = Qs + kAttWarps * kRtRows * D;
+  const int h = heads * D;
+  const int64_t seq = blockIdx.x;
+  const int head = blockIdx.y;
+  const T* base = qkv + seq * (int64_t)Tn * 3 * h + head * D;
+  for (int i = threadIdx.x; i < TP * (D / 4); i += blockDim.x) {  // rows >= T are zero: no masks in the loops below
+    const int t = i / (D / 4), c = (i % (D / 4)) * 4;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (t < Tn) {
+      kv = load4<T>(base + (size_t)t * 3 * h + h + c);
+      vv = load4<T>(base + (size_t)t * 3 * h + 2 * h + c);
+    }
+    *reinterpret_cast<float4*>(Ks + t * KS + c) = kv;
+    *reinterpret_cast<float4*>(Vs + t * D + c) = vv;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qw = Qs + warp * kRtRows * D;
+  float* pw = Ps + warp * kRtRows * PS;
+  const float scale = rsqrtf((float)D);
+  for (int t0 = warp * kRtRows; t0 < Tn; t0 += kAttWarps * kRtRows) {
+#pragma unroll
+    for (int r = 0; r < kRtRows * D / 4 / 32; ++r) {  // the 8 query rows (zero past the end)
+      const int idx = lane + 32 * r, row = idx / (D / 4), c = (idx % (D / 4)) * 4;
+      float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t0 + row < Tn) q = load4<T>(base + (size_t)(t0 + row) * 3 * h + c);
+      *reinterpret_cast<float4*>(qw + row * D + c) = q;
+    }
+    __syncwarp();
+    // ---- scores: lane owns keys lane + 32 k ----
+    float s[kRtRows][KPL];
+#pragma unroll
+    for (int i = 0; i < kRtRows; ++i)
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) s[i][k] = 0.f;
+#pragma unroll 2
+    for (int d = 0; d < D; d += 4) {
+      float4 q[kRtRows];
+#pragma unroll
+      for (int i = 0; i < kRtRows; ++i) q[i] = *reinterpret_cast<const float4*>(qw + i * D + d);
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) {
+        const float4 kk = *reinterpret_cast<const float4*>(Ks + (lane + 32 * k) * KS + d);
+#pragma unroll
+        for (int i = 0; i < kRtRows; ++i) {
+          s[i][k] = fmaf(q[i].x, kk.x, s[i][k]);
+          s[i][k] = fmaf(q[i].y, kk.y, s[i][k]);
+          s[i][k] = fmaf(q[i].z, kk.z, s[i][k]);
+          s[i][k] = fmaf(q[i].w, kk.w, s[i][k]);
+        }
+      }
+    }
+    // ---- softmax per row, probabilities to shared memory ----
+#pragma unroll
+    for (int i = 0; i < kRtRows; ++i) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) {
+        s[i][k] *= scale;
+        if (lane + k * 32 < Tn) m = fmaxf(m, s[i][k]);
+      }
+      m = warp_max(m);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) {
+        s[i][k] = lane + k * 32 < Tn ? expf(s[i][k] - m) : 0.f;
+        sum += s[i][k];
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int k = 0; k < KPL; ++k) pw[i * PS + lane + k * 32] = s[i][k] * inv;
+    }
+    __syncwarp();
+    // ---- P V: half-warp `half` owns rows 4 half .. 4 half + 3, each lane 4 channels ----
+    const int half = lane >> 4, c4 = (lane & 15) * 4;
+    float4 o[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) o[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* pr = pw + half * 4 * PS;
+    const int jend = (Tn + 3) & ~3;
+    for (int j4 = 0; j4 < jend; j4 += 4) {
+      float4 p[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) p[r] = *reinterpret_cast<const float4*>(pr + r * PS + j4);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const float4 v = *reinterpret_cast<const float4*>(Vs + (j4 + jj) * D + c4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float pj = jj == 0 ? p[r].x : jj == 1 ? p[r].y : jj == 2 ? p[r].z : p[r].w;
+          o[r].x = fmaf(pj, v.x, o[r].x);
+          o[r].y = fmaf(pj, v.y, o[r].y);
+          o[r].z = fmaf(pj, v.z, o[r].z);
+          o[r].w = fmaf(pj, v.w, o[r].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = t0 + half * 4 + r;
+      if (row < Tn) store4<T>(ctx + (seq * (int64_t)Tn + row) * h + head * D + c4, o[r]);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T, int KPL>
+int launch_rt(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
+  constexpr int D = 64, TP = KPL * 32;
+  const size_t smem = ((size_t)TP * (D + 4) + (size_t)TP * D + kAttWarps * kRtRows * D + kAttWarps * kRtRows * (TP + 4)) * sizeof(float);
+  auto kern = attention_rt_kernel<T, KPL>;
+  SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SVIT_CHECK_ARG(n_seq <= 0x7fffffff, "attention: too many sequences");
+  dim3 grid((unsigned)n_seq, heads);
+  kern<<<grid, kAttWarps * 32, smem, stream>>>((const T*)qkv, (T*)ctx, Tn, heads);
+  SVIT_LAUNCH_CHECK("attention_rt_kernel");
+  return SVIT_OK;
+}
+
+template <typename T>
+int dispatch_rt(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
+  switch ((Tn + 31) / 32) {
+    case 1: return launch_rt<T, 1>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 2: return launch_rt<T, 2>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 3: return launch_rt<T, 3>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 4: return launch_rt<T, 4>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 5: return launch_rt<T, 5>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 6: return launch_rt<T, 6>(qkv, ctx, n_seq, Tn, heads, stream);
+    case 7: return launch_rt<T, 7>(qkv, ctx, n_seq, Tn, heads, stream);
+    default: return launch_rt<T, 8>(qkv, ctx, n_seq, Tn, heads, stream);
+  }
+}
+
 template <typename T>
 int dispatch_d(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, int head_dim, cudaStream_t stream) {
+  static const bool no_rt = [] {  // SVIT_ATTENTION_NO_RT=1: the one-row-per-warp kernel for every head size (A/B)
+    const char* e = getenv("SVIT_ATTENTION_NO_RT");
+    return e && e[0] == '1';
+  }();
+  if (head_dim == 64 && (heads * head_dim) % 4 == 0 && !no_rt) return dispatch_rt<T>(qkv, ctx, n_seq, Tn, heads, stream);
   switch (head_dim) {
     case 32: return launch_att<T, 32>(qkv, ctx, n_seq, Tn, heads, stream);
     case 64: return launch_att<T, 64>(qkv, ctx, n_seq, Tn, heads, stream);
@@ -272,4 +445,11 @@ extern "C" int svit_attention(const void* qkv, void* ctx, int dtype, int64_t n_s
   SVIT_CHECK_ARG(qkv && ctx, "svit_attention: null pointer");
   SVIT_CHECK_ARG(n_seq >= 0 && heads >= 1, "svit_attention: bad sizes");
   return attention(qkv, ctx, dtype, n_seq, T, heads, head_dim, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int svit_attention_f16x3(const float* qkv, float* ctx, int64_t n_seq, int T, int heads, svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(qkv && ctx, "svit_attention_f16x3: null pointer");
+  SVIT_CHECK_ARG(n_seq >= 0 && heads >= 1, "svit_attention_f16x3: bad sizes");
+  return attention_split(qkv, ctx, n_seq, T, heads, static_cast<cudaStream_t>(stream));
 }

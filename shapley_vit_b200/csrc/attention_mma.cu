@@ -183,6 +183,166 @@ int dispatch_kt(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, cu
   return launch_mma<T, 16>(qkv, ctx, n_seq, Tn, heads, stream);
 }
 
+// ---- split-precision variant (SVIT_PREC_F16X3): fp32 in, fp32 out -------------------------------
+// Same tiling as attention_mma_kernel, but Q, K, V arrive in fp32 and are staged as fp16 hi + lo
+// tiles (x = hi + lo to ~2^-22); every product runs hi*hi + hi*lo + lo*hi into the fp32
+// accumulators -- scores and P V both -- with P split in registers after the fp32 softmax.
+// ~21 significant bits end to end at three MMAs per tile: the attention of the f16x3 mode.
+constexpr int kWarps3 = 8;
+
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16x2_sat(x, y);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = pack_f16x2_sat(x - hf.x, y - hf.y);
+}
+
+__device__ __forceinline__ void split8(const float* __restrict__ src, unsigned char* hi_tile, unsigned char* lo_tile,
+                                       uint32_t off) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+  uint4 hi, lo;
+  split2(a.x, a.y, hi.x, lo.x);
+  split2(a.z, a.w, hi.y, lo.y);
+  split2(b.x, b.y, hi.z, lo.z);
+  split2(b.z, b.w, hi.w, lo.w);
+  *reinterpret_cast<uint4*>(hi_tile + off) = hi;
+  *reinterpret_cast<uint4*>(lo_tile + off) = lo;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
+                                                                        int Tn, int heads) {
+  constexpr int TP = KT * 16;
+  constexpr int TILE = TP * 128;
+  extern __shared__ __align__(128) unsigned char att_raw[];
+  unsigned char* Qh = att_raw;  // Qh | Ql | Kh | Kl | Vh | Vl
+  const int h = heads * kD;
+  const int64_t seq = blockIdx.x;
+  const int head = blockIdx.y;
+  const float* base = qkv + seq * (int64_t)Tn * 3 * h + head * kD;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < TP * 8; i += kWarps3 * 32) {  // rows >= Tn are zero
+    const int row = i >> 3, chunk = i & 7;
+    const uint32_t off = tile_off(row, chunk);
+    if (row < Tn) {
+      const float* src = base + (size_t)row * 3 * h + chunk * 8;
+      split8(src, Qh, Qh + TILE, off);
+      split8(src + h, Qh + 2 * TILE, Qh + 3 * TILE, off);
+      split8(src + 2 * h, Qh + 4 * TILE, Qh + 5 * TILE, off);
+    } else {
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int m = 0; m < 6; ++m) *reinterpret_cast<uint4*>(Qh + m * TILE + off) = z;
+    }
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t q_base = smem_u32a(Qh), k_base = q_base + 2 * TILE, v_base = q_base + 4 * TILE;
+  const float sl2 = 0.125f * 1.4426950408889634f;  // d^-0.5 * log2(e), d = 64
+  const int lm = lane >> 3, lr = lane & 7;
+  using M = Mma<__half>;
+
+  for (int rt = warp; rt < KT; rt += kWarps3) {
+    const int r0 = rt * 16;
+    float S[2 * KT][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt) S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < kD / 16; ++ks) {
+      uint32_t ah[4], al[4];
+      const uint32_t qo = tile_off(r0 + lr + (lm & 1) * 8, ks * 2 + (lm >> 1));
+      ldsm_x4(ah[0], ah[1], ah[2], ah[3], q_base + qo);
+      ldsm_x4(al[0], al[1], al[2], al[3], q_base + TILE + qo);
+#pragma unroll
+      for (int np = 0; np < KT; ++np) {
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        const uint32_t ko = tile_off(np * 16 + lr + (lm >> 1) * 8, ks * 2 + (lm & 1));
+        ldsm_x4(h0, h1, h2, h3, k_base + ko);
+        ldsm_x4(l0, l1, l2, l3, k_base + TILE + ko);
+        M::run(S[2 * np], al, h0, h1);
+        M::run(S[2 * np], ah, l0, l1);
+        M::run(S[2 * np], ah, h0, h1);
+        M::run(S[2 * np + 1], al, h2, h3);
+        M::run(S[2 * np + 1], ah, l2, l3);
+        M::run(S[2 * np + 1], ah, h2, h3);
+      }
+    }
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (c >= Tn) S[nt][0] = S[nt][2] = -INFINITY;
+      if (c + 1 >= Tn) S[nt][1] = S[nt][3] = -INFINITY;
+      m0 = fmaxf(m0, fmaxf(S[nt][0], S[nt][1]));
+      m1 = fmaxf(m1, fmaxf(S[nt][2], S[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    const float o0 = m0 * sl2, o1 = m1 * sl2;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt) {
+      S[nt][0] = exp2f(fmaf(S[nt][0], sl2, -o0));
+      S[nt][1] = exp2f(fmaf(S[nt][1], sl2, -o0));
+      S[nt][2] = exp2f(fmaf(S[nt][2], sl2, -o1));
+      S[nt][3] = exp2f(fmaf(S[nt][3], sl2, -o1));
+      s0 += S[nt][0] + S[nt][1];
+      s1 += S[nt][2] + S[nt][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+    float O[kD / 8][4];
+#pragma unroll
+    for (int dt = 0; dt < kD / 8; ++dt) O[dt][0] = O[dt][1] = O[dt][2] = O[dt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      uint32_t ah[4], al[4];
+      split2(S[2 * kk][0] * i0, S[2 * kk][1] * i0, ah[0], al[0]);
+      split2(S[2 * kk][2] * i1, S[2 * kk][3] * i1, ah[1], al[1]);
+      split2(S[2 * kk + 1][0] * i0, S[2 * kk + 1][1] * i0, ah[2], al[2]);
+      split2(S[2 * kk + 1][2] * i1, S[2 * kk + 1][3] * i1, ah[3], al[3]);
+#pragma unroll
+      for (int dp = 0; dp < kD / 16; ++dp) {
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        const uint32_t vo = tile_off(kk * 16 + lr + (lm & 1) * 8, dp * 2 + (lm >> 1));
+        ldsm_x4_t(h0, h1, h2, h3, v_base + vo);
+        ldsm_x4_t(l0, l1, l2, l3, v_base + TILE + vo);
+        M::run(O[2 * dp], al, h0, h1);
+        M::run(O[2 * dp], ah, l0, l1);
+        M::run(O[2 * dp], ah, h0, h1);
+        M::run(O[2 * dp + 1], al, h2, h3);
+        M::run(O[2 * dp + 1], ah, l2, l3);
+        M::run(O[2 * dp + 1], ah, h2, h3);
+      }
+    }
+    const int ra = r0 + g, rb = r0 + g + 8;
+    float* out = ctx + seq * (int64_t)Tn * h + head * kD + 2 * t;
+#pragma unroll
+    for (int dt = 0; dt < kD / 8; ++dt) {
+      if (ra < Tn) *reinterpret_cast<float2*>(out + (size_t)ra * h + dt * 8) = make_float2(O[dt][0], O[dt][1]);
+      if (rb < Tn) *reinterpret_cast<float2*>(out + (size_t)rb * h + dt * 8) = make_float2(O[dt][2], O[dt][3]);
+    }
+  }
+}
+
+template <int KT>
+int launch_split(const float* qkv, float* ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
+  const size_t smem = (size_t)6 * KT * 16 * 128;
+  auto kern = attention_split_kernel<KT>;
+  SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)n_seq, heads);
+  kern<<<grid, kWarps3 * 32, smem, stream>>>(qkv, ctx, Tn, heads);
+  SVIT_LAUNCH_CHECK("attention_split_kernel");
+  return SVIT_OK;
+}
+
 }  // namespace
 
 // 16-bit operands, head_dim 64, T <= 256; qkv/ctx must be 16-byte aligned with h % 8 == 0
@@ -194,6 +354,18 @@ int attention_mma(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, 
   if (dtype == SVIT_F16) return dispatch_kt<__half>(qkv, ctx, n_seq, Tn, heads, stream);
   if (dtype == SVIT_BF16) return dispatch_kt<__nv_bfloat16>(qkv, ctx, n_seq, Tn, heads, stream);
   SVIT_FAIL(SVIT_ERR_ARG, "attention_mma: dtype %d is not a 16-bit type", dtype);
+}
+
+// fp32 qkv / ctx, head_dim 64, T <= 256: split-precision tensor-core attention (SVIT_PREC_F16X3)
+int attention_split(const float* qkv, float* ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
+  if (n_seq == 0) return SVIT_OK;
+  SVIT_CHECK_ARG(Tn >= 1 && Tn <= 256, "attention: T=%d out of range (1..256)", Tn);
+  SVIT_CHECK_ARG(n_seq <= 0x7fffffff, "attention: too many sequences");
+  if (!aligned16(qkv) || !aligned16(ctx)) SVIT_FAIL(SVIT_ERR_ALIGN, "attention: qkv/ctx must be 16-byte aligned");
+  if (Tn <= 16) return launch_split<1>(qkv, ctx, n_seq, Tn, heads, stream);
+  if (Tn <= 64) return launch_split<4>(qkv, ctx, n_seq, Tn, heads, stream);
+  if (Tn <= 208) return launch_split<13>(qkv, ctx, n_seq, Tn, heads, stream);
+  return launch_split<16>(qkv, ctx, n_seq, Tn, heads, stream);
 }
 
 }  // namespace svit

@@ -435,7 +435,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else {  // ===== softmax groups =====
     const int grp = warp >> 2;         // tile / TMEM buffer / staging buffer of this group
     const int quarter = warp & 3;      // TMEM lanes 32 * quarter .. + 31
-    const int gtid = quarter * 32 + lane;
     const uint32_t tbuf = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)grp * 256;
     uint8_t* ost = o_stage + (size_t)grp * kOBytes;
     const int row_in_tile = quarter * 32 + lane;
@@ -458,8 +457,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (quarter == 0) ATT_TRACE(4 * grp + 1);
 
       // ---- O = P V is on its way: make the staging tile reusable meanwhile ----
-      if (gtid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      // (each warp stores its own 32 rows, so nothing here needs a group-wide barrier)
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
 
       mbar_wait(&o_full[grp], par);
       tc_fence_after();
@@ -490,15 +490,16 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-      if (gtid == 0 && grp * 128 < Tn) {
+      __syncwarp();
+      if (lane == 0 && warp_valid) {
         const int seq = (int)(item / sh.heads), head = (int)(item % sh.heads);
-        tma_store_3d(&map_o, ost, head * kD, grp * 128, seq);  // rows >= T are clipped by the tensor map
+        // 32-row box; rows >= T are clipped by the tensor map
+        tma_store_3d(&map_o, ost + quarter * 4096, head * kD, grp * 128 + quarter * 32, seq);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (quarter == 0) ATT_TRACE(4 * grp + 3);
     }
-    if (gtid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -528,7 +529,7 @@ int launch_att(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, int
   // qkv [n_seq][T][3h]: boxes of 64 columns (one head of q, k or v) x rows
   if ((rc = encode_map_3d(&mq, dtype, qkv, 3 * h, Tn, n_seq, (uint64_t)3 * h * 2, (uint64_t)Tn * 3 * h * 2, kD, 128))) return rc;
   if ((rc = encode_map_3d(&mkv, dtype, qkv, 3 * h, Tn, n_seq, (uint64_t)3 * h * 2, (uint64_t)Tn * 3 * h * 2, kD, NK))) return rc;
-  if ((rc = encode_map_3d(&mo, dtype, ctx, h, Tn, n_seq, (uint64_t)h * 2, (uint64_t)Tn * h * 2, kD, 128))) return rc;
+  if ((rc = encode_map_3d(&mo, dtype, ctx, h, Tn, n_seq, (uint64_t)h * 2, (uint64_t)Tn * h * 2, kD, 32))) return rc;
   AttShape sh{};
   sh.T = Tn, sh.NK = NK, sh.heads = heads;
   sh.items = n_seq * heads;

@@ -153,6 +153,31 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ X, 
 
 }  // namespace
 
+// ---- fp32 -> [hi | lo] fp16 rows: the operand format of SVIT_PREC_F16X3 ---------------------------
+// x = hi + lo + O(2^-22 |x|) with hi = fp16(x), lo = fp16(x - hi) (x - hi is exact in fp32).
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ in, int64_t in_gs,
+                                                        __half* __restrict__ out, int64_t rows, int K, int64_t total) {
+  const int kv = K >> 3;  // 8-element pieces per row
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / kv;  // row over all groups
+    const int c = (int)(i - row * kv) << 3;
+    const int64_t g = row / rows, r = row - g * rows;
+    const float4* src = reinterpret_cast<const float4*>(in + g * in_gs + r * K + c);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __half2 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+      const float2 hf = __half22float2(hi[j]);
+      lo[j] = __floats2half2_rn(__fsub_rn(x[2 * j], hf.x), __fsub_rn(x[2 * j + 1], hf.y));
+    }
+    __half* dst = out + row * (2 * (int64_t)K) + c;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + K) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 int patchify(int dtype, const float* images, void* patches, int64_t n, int C, int H, int ps, cudaStream_t stream) {
   if (n == 0) return SVIT_OK;
   SVIT_CHECK_ARG(ps % 4 == 0 && H % ps == 0, "patchify: patch must be a multiple of 4 and divide the image");
@@ -168,6 +193,17 @@ int patchify(int dtype, const float* images, void* patches, int64_t n, int C, in
     default: SVIT_FAIL(SVIT_ERR_ARG, "patchify: bad dtype %d", dtype);
   }
   SVIT_LAUNCH_CHECK("patchify_kernel");
+  return SVIT_OK;
+}
+
+int split_f16(const float* in, int64_t in_gs, void* out, int G, int64_t rows, int K, cudaStream_t stream) {
+  SVIT_CHECK_ARG(K % 8 == 0 && in_gs % 4 == 0, "split_f16: K and the group stride must be multiples of 8 / 4");
+  const int64_t total = (int64_t)G * rows * (K / 8);
+  if (total == 0) return SVIT_OK;
+  const int block = 256;
+  const int grid = (int)std::min<int64_t>((total + block - 1) / block, (int64_t)sm_count() * 16);
+  split_f16_kernel<<<grid, block, 0, stream>>>(in, in_gs, static_cast<__half*>(out), rows, K, total);
+  SVIT_LAUNCH_CHECK("split_f16_kernel");
   return SVIT_OK;
 }
 
@@ -226,4 +262,12 @@ extern "C" int svit_layernorm(const float* x, int64_t x_gs, int64_t x_ld, const 
     SVIT_FAIL(SVIT_ERR_ALIGN, "svit_layernorm: pointers must be 16-byte aligned");
   return layernorm(x, x_gs, x_ld, gamma, beta, param_gs, y, y_gs, y_ld, out_dtype, G, rows, h, eps,
                    static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int svit_split_f16(const float* in, int64_t in_gs, void* out, int G, int64_t rows, int K,
+                              svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(in && out && G >= 1 && rows >= 0 && K >= 8, "svit_split_f16: bad arguments");
+  if (!aligned16(in) || !aligned16(out)) SVIT_FAIL(SVIT_ERR_ALIGN, "svit_split_f16: pointers must be 16-byte aligned");
+  return split_f16(in, in_gs, out, G, rows, K, static_cast<cudaStream_t>(stream));
 }

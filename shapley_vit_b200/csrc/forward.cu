@@ -35,6 +35,7 @@ struct svit_plan {
   bool full_last_layer = false;  // SVIT_FULL_LAST_LAYER=1: compute every token of the last layer (A/B and tests)
   // workspace byte offsets for (max_c, max_b)
   size_t off_x = 0, off_xn = 0, off_qkv = 0, off_ctx = 0, off_h = 0, ws_bytes = 0;
+  size_t off_sa = 0, off_sb = 0;  // SVIT_PREC_F16X3: [hi | lo] fp16 copies of the current GEMM's A and B operands
   // optional per-kernel-class device timing (svit_plan_timing_begin / _end)
   bool timing = false;
   struct Span {
@@ -42,6 +43,7 @@ struct svit_plan {
     int cls;
     double work;  // flops (GEMM, attention) or bytes (others)
   };
+  void *split_a = nullptr, *split_b = nullptr;  // set per svit_forward_batched call (workspace + off_sa / off_sb)
   std::vector<Span> spans;
   std::vector<cudaEvent_t> pool;
   size_t pool_used = 0;
@@ -53,7 +55,8 @@ namespace {
 int operand_dtype_of(int precision) {
   switch (precision) {
     case SVIT_PREC_F32:
-    case SVIT_PREC_TF32: return SVIT_F32;
+    case SVIT_PREC_TF32:
+    case SVIT_PREC_F16X3: return SVIT_F32;
     case SVIT_PREC_BF16: return SVIT_BF16;
     case SVIT_PREC_F16: return SVIT_F16;
     default: return -1;
@@ -94,6 +97,15 @@ int gemm_dispatch(svit_plan* p, const void* A, int64_t a_gs, const void* B, int6
   Timed t(p, stream, SVIT_CLS_GEMM, 2.0 * G * M * (double)N * K);
   if (p->precision == SVIT_PREC_F32 || p->force_simt)
     return gemm_simt(p->operand_dtype, A, a_gs, B, b_gs, G, M, N, K, epi, stream);
+  if (p->precision == SVIT_PREC_F16X3) {
+    // fp32 operands -> [hi | lo] fp16 rows in the plan's scratch, then hi*hi + hi*lo + lo*hi on the tensor cores
+    const int ga = a_gs ? G : 1;
+    int rc;
+    if ((rc = split_f16(static_cast<const float*>(A), a_gs, p->split_a, ga, M, K, stream))) return rc;
+    if ((rc = split_f16(static_cast<const float*>(B), b_gs, p->split_b, G, N, K, stream))) return rc;
+    return gemm_tc(p->precision, p->split_a, a_gs ? (int64_t)M * 2 * K : 0, p->split_b, (int64_t)N * 2 * K, G, M, N, K, epi,
+                   stream);
+  }
   return gemm_tc(p->precision, A, a_gs, B, b_gs, G, M, N, K, epi, stream);
 }
 
@@ -143,6 +155,12 @@ extern "C" int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_
   p->off_qkv = take(rows * 3 * cfg->hidden * es);
   p->off_ctx = take(rows * cfg->hidden * es);
   p->off_h = take(rows * cfg->ff * es);
+  if (precision == SVIT_PREC_F16X3) {
+    const size_t kmax = (size_t)std::max(std::max(cfg->hidden, cfg->ff), p->pd);
+    const size_t nk = std::max((size_t)cfg->hidden * cfg->ff, std::max((size_t)3 * cfg->hidden * cfg->hidden, (size_t)cfg->hidden * p->pd));
+    p->off_sa = take(rows * kmax * 4);  // [rows, 2K] fp16
+    p->off_sb = take((size_t)max_coalitions * nk * 4);
+  }
   p->ws_bytes = off;
   *out = p;
   return SVIT_OK;
@@ -195,6 +213,8 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
   void* QKV = ws + plan->off_qkv;
   void* CTX = ws + plan->off_ctx;
   void* H = ws + plan->off_h;
+  plan->split_a = ws + plan->off_sa;
+  plan->split_b = ws + plan->off_sb;
   const char* wm = static_cast<const char*>(wmat);
   auto mat = [&](int kind, int layer) -> const void* { return wm + (size_t)L.find(kind, layer) * es; };
   auto vec = [&](int kind, int layer) -> const float* { return wvec + L.find(kind, layer); };
@@ -279,7 +299,11 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
     }
     {
       Timed t(plan, stream, SVIT_CLS_ATTENTION, 4.0 * C * B * (double)T * T * h);
-      if ((rc = attention(QKV, CTX, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream))) return rc;
+      if (plan->precision == SVIT_PREC_F16X3 && h / cfg.heads == 64)  // split-precision tensor-core attention
+        rc = attention_split(static_cast<const float*>(QKV), static_cast<float*>(CTX), (int64_t)C * B, T, cfg.heads, stream);
+      else
+        rc = attention(QKV, CTX, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream);
+      if (rc) return rc;
     }
     {
       svit_epilogue e{};
@@ -328,9 +352,10 @@ extern "C" int svit_gemm(int precision, const void* A, int64_t a_gs, const void*
   const int odt = operand_dtype_of(precision);
   SVIT_CHECK_ARG(odt >= 0, "svit_gemm: unknown precision %d", precision);
   SVIT_CHECK_ARG(out_dtype == SVIT_F32 || out_dtype == odt, "svit_gemm: out_dtype must be f32 or the operand dtype");
+  // (SVIT_PREC_F16X3: A and B arrive pre-split, see svit_split_f16; the output is fp32)
   EpiArgs ea = make_epi(epi, out, out_gs, out_dtype, M, N);
   const char* env = getenv("SVIT_FORCE_SIMT_GEMM");
-  if (precision == SVIT_PREC_F32 || (env && env[0] == '1'))
+  if (precision == SVIT_PREC_F32 || (precision != SVIT_PREC_F16X3 && env && env[0] == '1'))
     return gemm_simt(odt, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
   return gemm_tc(precision, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
 }

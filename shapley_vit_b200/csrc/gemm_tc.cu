@@ -209,7 +209,18 @@ struct TcShape {
   int tiles_m, tiles_n, num_kb;
   int64_t total_tiles;
   int a_grouped;  // 0: A shared by all groups
+  int split_kb;   // > 0: operands are [hi | lo] halves of split_kb k-blocks each; the K loop runs hi*hi, hi*lo, lo*hi
 };
+
+// k-block of A and of B read by step kb of the K loop (identity unless the operands are split)
+__device__ __forceinline__ void split_blocks(const TcShape& sh, int kb, int& ka, int& kw) {
+  ka = kb, kw = kb;
+  if (sh.split_kb) {
+    const int nk = sh.split_kb;
+    if (kb >= 2 * nk) ka = kb - nk, kw = kb - 2 * nk;  // A lo * B hi
+    else if (kb >= nk) ka = kb - nk;                   // A hi * B lo
+  }
+}
 
 // ---- packed fp32x2 arithmetic (FFMA2: two IEEE fp32 FMAs per issue slot on sm_100) ------------
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -567,9 +578,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          const int k0 = kb * (KIND == 0 ? 64 : 32);
-          tma_load_3d(sa, &tma_a, &full_bar[s], k0, m0, sh.a_grouped ? g : 0);
-          tma_load_3d(sa + C::A_BYTES, &tma_b, &full_bar[s], k0, n0, g);
+          constexpr int BKE = KIND == 0 ? 64 : 32;
+          int ka, kw;
+          split_blocks(sh, kb, ka, kw);
+          tma_load_3d(sa, &tma_a, &full_bar[s], ka * BKE, m0, sh.a_grouped ? g : 0);
+          tma_load_3d(sa + C::A_BYTES, &tma_b, &full_bar[s], kw * BKE, n0, g);
         }
         __syncwarp();
         if (++s == C::STAGES) s = 0, ph ^= 1;
@@ -708,9 +721,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-          const int k0 = kb * (KIND == 0 ? 64 : 32);
-          tma_load_3d_pair(sa, &tma_a, full0 + 8u * s, k0, m0, sh.a_grouped ? g : 0);
-          tma_load_3d_pair(sa + C::A_BYTES, &tma_b, full0 + 8u * s, k0, n0, g);
+          constexpr int BKE = KIND == 0 ? 64 : 32;
+          int ka, kw;
+          split_blocks(sh, kb, ka, kw);
+          tma_load_3d_pair(sa, &tma_a, full0 + 8u * s, ka * BKE, m0, sh.a_grouped ? g : 0);
+          tma_load_3d_pair(sa + C::A_BYTES, &tma_b, full0 + 8u * s, kw * BKE, n0, g);
         }
         __syncwarp();
         if (++s == C::STAGES) s = 0, ph ^= 1;
@@ -840,9 +855,12 @@ int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const TcShape& sh, 
 
 int gemm_tc(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, int G, int M, int N, int K,
             const EpiArgs& epi, cudaStream_t stream) {
+  const bool split = precision == SVIT_PREC_F16X3;  // operands pre-split into [hi | lo] fp16 rows of 2K
   const int dtype = precision == SVIT_PREC_TF32 ? SVIT_F32 : precision == SVIT_PREC_BF16 ? SVIT_BF16 : SVIT_F16;
-  SVIT_CHECK_ARG(precision == SVIT_PREC_TF32 || precision == SVIT_PREC_BF16 || precision == SVIT_PREC_F16,
+  SVIT_CHECK_ARG(precision == SVIT_PREC_TF32 || precision == SVIT_PREC_BF16 || precision == SVIT_PREC_F16 || split,
                  "gemm_tc: precision %d has no tensor-core path", precision);
+  SVIT_CHECK_ARG(!split || K % 64 == 0, "gemm_tc: f16x3 needs K %% 64 == 0 (K=%d)", K);
+  const int Kphys = split ? 2 * K : K;  // row length of the operands in memory
   const int es = dtype_size(dtype);
   if (!aligned16(A) || !aligned16(B) || ((int64_t)K * es) % 16 || (a_gs * es) % 16 || (b_gs * es) % 16)
     SVIT_FAIL(SVIT_ERR_ALIGN, "gemm_tc: operands must be 16-byte aligned with K*elt and group strides multiples of 16 bytes");
@@ -857,12 +875,14 @@ int gemm_tc(int precision, const void* A, int64_t a_gs, const void* B, int64_t b
   const bool pair = BN == 256 && M >= 2 * BM && !no_pair;  // CTA-pair kernel: each CTA stages half of the B tile
   CUtensorMap ma, mb;
   int rc;
-  if ((rc = make_map(&ma, dtype, A, M, K, a_gs ? G : 1, a_gs, BM))) return rc;
-  if ((rc = make_map(&mb, dtype, B, N, K, b_gs ? G : 1, b_gs, pair ? BN / 2 : BN))) return rc;
+  if ((rc = make_map(&ma, dtype, A, M, Kphys, a_gs ? G : 1, a_gs, BM))) return rc;
+  if ((rc = make_map(&mb, dtype, B, N, Kphys, b_gs ? G : 1, b_gs, pair ? BN / 2 : BN))) return rc;
   TcShape sh{};
   sh.G = G, sh.M = M, sh.N = N, sh.K = K;
   const int bk = 128 / es;
   sh.num_kb = (K + bk - 1) / bk;
+  sh.split_kb = split ? sh.num_kb : 0;
+  if (split) sh.num_kb *= 3;
   sh.a_grouped = a_gs ? 1 : 0;
   SVIT_CHECK_ARG(b_gs != 0 || G == 1, "gemm_tc: B must be grouped when G > 1");
   // instruction descriptor: D fp32, A/B format, both K-major, N, M

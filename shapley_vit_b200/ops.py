@@ -10,7 +10,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import BF16, F16, F32, PREC_BF16, PREC_F16, PREC_F32, PREC_TF32, EpilogueC, check
+from ._lib import BF16, F16, F32, PREC_BF16, PREC_F16, PREC_F16X3, PREC_F32, PREC_TF32, EpilogueC, check
 
 TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 SVIT_DTYPE = {v: k for k, v in TORCH_DTYPE.items()}
@@ -125,6 +125,29 @@ def attention(qkv: torch.Tensor, heads: int) -> torch.Tensor:
     return ctx
 
 
+def attention_f16x3(qkv: torch.Tensor, heads: int) -> torch.Tensor:
+    """fp32 qkv [n_seq, T, 3h] -> fp32 ctx: the split-precision tensor-core attention of PREC_F16X3 (head_dim 64)."""
+    _cuda(qkv, "qkv")
+    qkv = qkv.contiguous()
+    n_seq, T, h3 = qkv.shape
+    h = h3 // 3
+    if qkv.dtype != torch.float32 or h // heads != 64:
+        raise ValueError("attention_f16x3 takes fp32 qkv with head_dim 64")
+    ctx = torch.empty((n_seq, T, h), dtype=torch.float32, device=qkv.device)
+    check(_lib.load().svit_attention_f16x3(_ptr(qkv), _ptr(ctx), n_seq, T, heads, _stream(qkv)))
+    return ctx
+
+
+def split_f16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [G, rows, K] -> fp16 [G, rows, 2K] = [hi | lo] per row, the operand format of PREC_F16X3."""
+    _cuda(x, "x")
+    x = x.contiguous()
+    G, rows, K = x.shape
+    out = torch.empty((G, rows, 2 * K), dtype=torch.float16, device=x.device)
+    check(_lib.load().svit_split_f16(_ptr(x), rows * K, _ptr(out), G, rows, K, _stream(x)))
+    return out
+
+
 def gemm(precision: int, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, gelu: bool = False, out_dtype: Optional[torch.dtype] = None,
          rowvec: Optional[torch.Tensor] = None, rows_in: int = 0, rows_out: int = 0, row_shift: int = 0,
@@ -136,9 +159,12 @@ def gemm(precision: int, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.
     A, B = A.contiguous(), B.contiguous()
     G, N, K = B.shape
     M = A.shape[1]
-    a_gs = 0 if (A.shape[0] == 1 and G > 1) else M * K
-    m_out = M if rows_in <= 0 else (M // rows_in) * rows_out
     out_dtype = out_dtype or A.dtype
+    kp = K                      # row length of the operands in memory
+    if precision == PREC_F16X3:  # fp32 in, split here; the library takes the [hi | lo] rows
+        A, B, kp = split_f16(A), split_f16(B), 2 * K
+    a_gs = 0 if (A.shape[0] == 1 and G > 1) else M * kp
+    m_out = M if rows_in <= 0 else (M // rows_in) * rows_out
     if out is None:
         out = torch.zeros((G, m_out, N), dtype=out_dtype, device=A.device)
     epi = EpilogueC()
@@ -152,7 +178,7 @@ def gemm(precision: int, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.
     if residual is not None:
         epi.residual, epi.residual_gs = residual.data_ptr(), m_out * N
     epi.gelu, epi.rows_in, epi.rows_out, epi.row_shift = int(gelu), rows_in, rows_out, row_shift
-    check(_lib.load().svit_gemm(precision, _ptr(A), a_gs, _ptr(B), N * K, _ptr(out), m_out * N, SVIT_DTYPE[out.dtype],
+    check(_lib.load().svit_gemm(precision, _ptr(A), a_gs, _ptr(B), N * kp, _ptr(out), m_out * N, SVIT_DTYPE[out.dtype],
                                 G, M, N, K, C.byref(epi), _stream(A)))
     return out
 

@@ -74,7 +74,7 @@ _NEW_FLAGS = [
     (("--vit-size", "--vit_size"), dict(type=str, default="base", help="tiny | small | base | large")),
     (("--image-size", "--image_size"), dict(type=int, default=224, help="ViT input resolution")),
     (("--num-classes", "--num_classes"), dict(type=int, default=4, help="classifier width (reference: 4)")),
-    (("--dtype",), dict(type=str, default="f16", help="GEMM operand precision: f16 | bf16 | tf32 | f32")),
+    (("--dtype",), dict(type=str, default="f16", help="GEMM operand precision: f16 | bf16 | tf32 | f16x3 | f32")),
     (("--synthetic",), dict(action=_STORE_TRUE, default=False, help="synthetic validation set and client models")),
     (("--val-size", "--val_size"), dict(type=int, default=1000, help="synthetic validation images")),
 ]

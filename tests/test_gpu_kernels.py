@@ -168,6 +168,20 @@ def test_attention_fp32(ops, T, heads, d):
         assert (got16 - want16).abs().max() < tol
 
 
+@pytest.mark.parametrize("T,heads,n_seq", [(5, 3, 4), (197, 12, 9), (16, 2, 3), (17, 1, 3), (64, 3, 3), (208, 2, 3),
+                                           (209, 1, 3), (256, 1, 5)])
+def test_attention_f16x3(ops, T, heads, n_seq):
+    """Split-precision tensor-core attention (fp32 in / out, hi*hi + hi*lo + lo*hi): fp32-grade against fp64."""
+    d, h = 64, heads * 64
+    qkv = gen(n_seq, T, 3 * h, seed=T + 1)
+    q, k, v = (t.double().view(n_seq, T, heads, d).transpose(1, 2) for t in qkv.split(h, dim=2))
+    want = (torch.softmax(q @ k.transpose(2, 3) * d ** -0.5, dim=-1) @ v).transpose(1, 2).reshape(n_seq, T, h)
+    got = ops.attention_f16x3(qkv.cuda(), heads).cpu().double()
+    err = (got - want).abs().max().item()
+    print(f"attention f16x3 T={T}: max err {err:.3e}")
+    assert err < 1e-5
+
+
 @pytest.mark.parametrize("T,heads,n_seq", [(197, 12, 40), (129, 3, 5), (256, 2, 7), (144, 1, 300), (250, 4, 3)])
 @pytest.mark.parametrize("dt,tol", [(torch.float16, 4e-3), (torch.bfloat16, 3e-2)])
 def test_attention_tcgen05(ops, T, heads, n_seq, dt, tol):
@@ -241,6 +255,35 @@ def test_gemm_tcgen05_matches_cuda_core_gemm(ops, prec_name, G, M, N, K, monkeyp
         tol = 1e-4 * (K / 64) ** 0.5
     err = (got.double() - want).abs().max().item()
     assert err < tol, f"max err {err}"
+
+
+@pytest.mark.parametrize("G,M,N,K", [(1, 128, 256, 64), (2, 300, 768, 768), (1, 1000, 768, 3072), (2, 6000, 768, 256),
+                                     (3, 197 * 4, 2304, 768), (2, 640, 576, 192), (2, 257, 512, 128)])
+def test_gemm_f16x3_split_precision(ops, G, M, N, K):
+    """SVIT_PREC_F16X3: fp32 operands split into fp16 hi + lo, three tcgen05 passes.  Held against the
+    fp64 product of the UNROUNDED fp32 operands: >= 8x closer than one fp16 pass can be (measured 15-80x).
+    What is left is the tensor core's own fp32 accumulation, which truncates (round toward zero) at every
+    16-deep step: a bias that grows like K^1.5 on these all-positive-variance inputs."""
+    from shapley_vit_b200._lib import PRECISIONS
+
+    A, B = gen(G, M, K, seed=M), gen(G, N, K, seed=N) * 0.05
+    bias, res = gen(G, N, seed=3), gen(G, M, N, seed=4)
+    got = ops.gemm(PRECISIONS["f16x3"], A.cuda(), B.cuda(), bias=bias.cuda(), residual=res.cuda(),
+                   out_dtype=torch.float32).cpu()
+    want = ref_gemm(A, B, bias, res)
+    err = (got.double() - want).abs().max().item()
+    one_pass = (ref_gemm(A.half().float(), B.half().float(), bias, res) - want).abs().max().item()
+    print(f"f16x3 max err {err:.3e} (one fp16 pass: {one_pass:.3e})")
+    assert err < max(1e-5, 4e-6 * (K / 64) ** 1.5) and err < one_pass / 8
+
+
+def test_split_f16_halves(ops):
+    x = torch.cat([gen(2, 37, 64, seed=1), gen(2, 37, 64, seed=2) * 1e-3], dim=2)
+    got = ops.split_f16(x.cuda()).cpu()
+    K = x.shape[2]
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    assert torch.equal(got[..., :K], hi) and torch.equal(got[..., K:], lo)
 
 
 @pytest.mark.parametrize("prec_name", ["f16", "tf32"])
