@@ -17,6 +17,8 @@ so parity is pinned on outputs of the reference's own code driven here through
   8 images: logits for three coalitions (pins the restated forward at the
   BASELINE config 2 geometry);
 * ``estimators``  -- every reference estimator on table-driven toy games;
+* ``round_select`` -- the three MILP round selectors (fed_client_contribution/milp.py) on seeded
+  selection matrices;
 * ``lazy_rounds`` -- the multi-round reconstruction ``compute_utilities_lazy``
   (utils_fed_shapley.py:146-196) on 3 clients x 3 FL rounds with a selection matrix.
 
@@ -302,11 +304,51 @@ def golden_lazy(ref):
     print("lazy_rounds done")
 
 
+def round_select_cases():
+    """Seeded selection matrices (every client takes part at least once) and selector settings."""
+    cases = []
+    rng = np.random.RandomState(7)
+    for T, n, kmax, gamma, weighted in ((6, 3, 2, 0.5, False), (10, 4, 3, 0.3, False), (8, 5, None, 0.5, True),
+                                        (12, 4, 5, 0.9, True), (5, 3, 1, 0.0, False), (9, 6, 4, 1.0, False)):
+        sel = (rng.rand(T, n) < 0.6).astype(float)
+        for i in range(n):
+            if sel[:, i].sum() == 0:
+                sel[rng.randint(T), i] = 1.0
+        w = None
+        if weighted:
+            w = rng.rand(T)
+            w = w / w.sum()
+        cases.append({"selection": sel.tolist(), "kmax": kmax, "gamma": gamma, "weights": None if w is None else w.tolist()})
+    return cases
+
+
+def golden_round_select(ref):
+    """The three MILP round selectors of the reference (fed_client_contribution/milp.py) on seeded cases."""
+    import importlib
+
+    milp = importlib.import_module("refshapleyserver.fed_client_contribution.milp")
+    out = []
+    for case in round_select_cases():
+        sel = np.array(case["selection"])
+        rec = dict(case)
+        for name in ("MILP_Shapley", "MILP_Shapley_Two_Sided", "MILP_Shapley_Two_Sided_Approx"):
+            w = None if case["weights"] is None else np.array(case["weights"])
+            ok, fun, x = getattr(milp, name)(sel, case["kmax"], case["gamma"], w).solve()
+            rec[name] = {"success": bool(ok), "fun": None if fun is None else float(fun),
+                         "x": None if x is None else [float(v) for v in x]}
+        out.append(rec)
+    with open(os.path.join(GOLD, "round_select.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("round_select done")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = ref_shim.load()
-    which = sys.argv[1:] or ["estimators", "cfg1", "base", "lazy"]
+    which = sys.argv[1:] or ["estimators", "cfg1", "base", "lazy", "rounds"]
+    if "rounds" in which:
+        golden_round_select(ref)
     if "estimators" in which:
         golden_estimators(ref)
     if "cfg1" in which:
