@@ -125,8 +125,32 @@ def reference_member_order(coalition: Iterable[int], selection: Sequence[bool] |
 # M1: HF ViTForImageClassification forward, restated on a raw state_dict
 # --------------------------------------------------------------------------- #
 
+def split_peft_state_dict(sd: Dict[str, torch.Tensor]):
+    """PEFT-LoRA state_dict (reference start.py:274-283: r=16, alpha=8 on query/value, classifier in
+    modules_to_save; DataParallel ``module.`` prefix) -> (HF-keyed base state_dict, {(layer, proj): (A, B)}).
+    PEFT is absent from the build container; the key scheme is the published one of peft.tuners.lora
+    (``base_model.model.<path>.{base_layer.weight, lora_A.<adapter>.weight, lora_B.<adapter>.weight}``,
+    ``classifier.{original_module, modules_to_save.<adapter>}``).  PARITY UNPINNED for this function."""
+    import re
+
+    hf, lora = {}, {}
+    for k, v in sd.items():
+        while k.startswith("module.") or k.startswith("base_model.model."):
+            k = k.split(".", 1)[1] if k.startswith("module.") else k[len("base_model.model."):]
+        m = re.match(r"^vit\.encoder\.layer\.(\d+)\.attention\.attention\.(\w+)\.lora_([AB])\.[^.]+\.weight$", k)
+        if m:
+            a_b = lora.setdefault((int(m.group(1)), m.group(2)), [None, None])
+            a_b[0 if m.group(3) == "A" else 1] = v
+            continue
+        if k.startswith("classifier.original_module."):
+            continue
+        k = re.sub(r"^classifier\.modules_to_save\.[^.]+\.", "classifier.", k.replace(".base_layer.", "."))
+        hf[k] = v
+    return hf, {key: (a, b) for key, (a, b) in lora.items()}
+
+
 def vit_forward(sd: Dict[str, torch.Tensor], cfg, images: torch.Tensor,
-                return_hidden: bool = False):
+                return_hidden: bool = False, lora=None, lora_scaling: float = 0.5):
     """logits = ViTForImageClassification(images).logits with weights ``sd``.
 
     Restates transformers 5.5.0 models/vit/modeling_vit.py: embeddings :100-128
@@ -150,6 +174,11 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg, images: torch.Tensor,
         q = F.linear(y, sd[p + "attention.attention.query.weight"], sd[p + "attention.attention.query.bias"])
         k = F.linear(y, sd[p + "attention.attention.key.weight"], sd[p + "attention.attention.key.bias"])
         v = F.linear(y, sd[p + "attention.attention.value.weight"], sd[p + "attention.attention.value.bias"])
+        if lora:  # peft lora.Linear.forward in eval mode: base(x) + lora_B(lora_A(x)) * (alpha / r), unmerged
+            if (i, "query") in lora:
+                q = q + F.linear(F.linear(y, lora[(i, "query")][0]), lora[(i, "query")][1]) * lora_scaling
+            if (i, "value") in lora:
+                v = v + F.linear(F.linear(y, lora[(i, "value")][0]), lora[(i, "value")][1]) * lora_scaling
         q, k, v = (t.view(B, -1, nh, hd).transpose(1, 2) for t in (q, k, v))
         att = torch.softmax(torch.matmul(q, k.transpose(2, 3)) * scaling, dim=-1)
         ctx = torch.matmul(att, v).transpose(1, 2).reshape(B, -1, h)

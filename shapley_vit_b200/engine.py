@@ -144,6 +144,14 @@ class CoalitionEngine:
         return self.coalition_batch * self.n_clients * 4
 
     # ------------------------------------------------------------------ #
+    def _aggregate_batch(self, ratios: torch.Tensor, Cn: int) -> None:
+        """K1: W_S = W_0 + sum_j r_j Delta_j for the batch's coalitions into wvec / wmat (both regions)."""
+        V, Mz = self.lay.vec_size, self.lay.mat_size
+        w0v = self.w0[:V] if self.w0 is not None else None
+        w0m = self.w0[V:] if self.w0 is not None else None
+        ops.aggregate(self.deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
+        ops.aggregate(self.deltas[:, V:], w0m, ratios, out=self.wmat[:Cn], P=Mz)
+
     def _run_batch(self, ratio_rows: Sequence[Sequence[float]]) -> Tuple[torch.Tensor, torch.Tensor]:
         """One batch of <= coalition_batch coalitions given their dense ratio rows."""
         Cn = len(ratio_rows)
@@ -151,14 +159,10 @@ class CoalitionEngine:
         # FedAvg ratios: fp64 on the host (as the reference computes them), rounded once to fp32;
         # svit_aggregate copies them into its kernel parameters (no separate H2D copy)
         ratios = torch.as_tensor(ratio_rows, dtype=torch.float64).to(torch.float32)
-        V, Mz = lay.vec_size, lay.mat_size
-        w0v = self.w0[:V] if self.w0 is not None else None
-        w0m = self.w0[V:] if self.w0 is not None else None
         if self.profile:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        ops.aggregate(self.deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
-        ops.aggregate(self.deltas[:, V:], w0m, ratios, out=self.wmat[:Cn], P=Mz)
+        self._aggregate_batch(ratios, Cn)
         if self.profile:
             e1.record()
             self.agg_spans.append((e0, e1))

@@ -17,7 +17,7 @@ from typing import Dict, FrozenSet, Iterable, List, Optional, Sequence
 
 import torch
 
-from . import _lib, dist
+from . import _lib, dist, lora
 from .engine import CoalitionEngine, ValidationSet
 from .fl import _clean_keys, _state_dict_of, config_of
 
@@ -59,17 +59,26 @@ class Game:
             a = self.server_args
             precision = _lib.PRECISIONS[a.get("precision", "f16")]
             device = a.get("device", dist.default_device())
-            cfg = config_of(self.init_server_model, a.get("heads"))
             w0 = _clean_keys(_state_dict_of(self.init_server_model))
+            is_lora = lora.is_lora_state_dict(w0)          # PEFT-wrapped model (reference start.py:274-283)
+            if is_lora:
+                from .models.vit import infer_config
+                cfg = getattr(self.init_server_model, "cfg", None) or infer_config(lora.split_state_dict(w0)[0],
+                                                                                  heads=a.get("heads"))
+            else:
+                cfg = config_of(self.init_server_model, a.get("heads"))
             deltas = []
             for j in range(self._n_all):
                 d = self.client_models[j]
                 deltas.append(_clean_keys(d) if d is not None else {k: torch.zeros_like(v) for k, v in w0.items()})
             loader = self.server.valid_loader
             val = loader if isinstance(loader, ValidationSet) else ValidationSet.from_loader(cfg, loader, precision, device)
-            self._engine = CoalitionEngine(cfg, w0, deltas, val, precision=precision,
-                                           coalition_batch=a.get("coalition_batch", 8),
-                                           image_chunk=a.get("image_chunk", 128), device=device)
+            kw = dict(precision=precision, coalition_batch=a.get("coalition_batch", 8),
+                      image_chunk=a.get("image_chunk", 128), device=device)
+            if is_lora:
+                self._engine = lora.LoraCoalitionEngine(cfg, w0, deltas, val, lora_alpha=a.get("lora_alpha", 8.0), **kw)
+            else:
+                self._engine = CoalitionEngine(cfg, w0, deltas, val, **kw)
         return self._engine
 
     def _n_val(self) -> int:

@@ -43,6 +43,51 @@ def make_client_state_dict(w0: Dict[str, torch.Tensor], client: int, seed: int =
     return out
 
 
+def make_peft_state_dicts(cfg: VitConfig, n_clients: int, seed: int = 0, r: int = 16, frozen_base: bool = True,
+                          prefix: str = "module.base_model.model.", sigma: float = 0.02):
+    """Synthetic stand-in for the author's setup (reference start.py:274-283): a PEFT-LoRA wrapped ViT
+    state_dict (query / value wrapped, rank r; classifier in modules_to_save) for the initial model and
+    for ``n_clients`` locally trained models.  Initial model: A random, B = 0 (PEFT's init); clients: A, B
+    and the classifier moved, the base frozen unless ``frozen_base`` is False.
+    Returns (w0_sd, [client_sd, ...]) with PEFT key names."""
+    base = make_state_dict(cfg, seed)
+    h = cfg.hidden
+
+    def wrap(sd, lora, cls_w, cls_b):
+        out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        for k, v in sd.items():
+            m = k.endswith("attention.attention.query.weight") or k.endswith("attention.attention.value.weight") \
+                or k.endswith("attention.attention.query.bias") or k.endswith("attention.attention.value.bias")
+            if m:
+                stem, leaf = k.rsplit(".", 1)
+                out[f"{prefix}{stem}.base_layer.{leaf}"] = v
+                if leaf == "weight":
+                    a, b = lora[stem]
+                    out[f"{prefix}{stem}.lora_A.default.weight"] = a
+                    out[f"{prefix}{stem}.lora_B.default.weight"] = b
+            elif k.startswith("classifier."):
+                leaf = k.split(".", 1)[1]
+                out[f"{prefix}classifier.original_module.{leaf}"] = v
+                out[f"{prefix}classifier.modules_to_save.default.{leaf}"] = cls_w if leaf == "weight" else cls_b
+            else:
+                out[prefix + k] = v
+        return out
+
+    g = torch.Generator().manual_seed(1_000_003 * seed + 31)
+    stems = [f"vit.encoder.layer.{i}.attention.attention.{t}" for i in range(cfg.layers) for t in ("query", "value")]
+    lora0 = {st: (torch.randn(r, h, generator=g) * (1.0 / h) ** 0.5, torch.zeros(h, r)) for st in stems}
+    w0 = wrap(base, lora0, base["classifier.weight"], base["classifier.bias"])
+    clients = []
+    for j in range(n_clients):
+        gj = torch.Generator().manual_seed(1_000_003 * seed + 7919 * (j + 1) + 5)
+        lj = {st: (a + sigma * torch.randn(a.shape, generator=gj), 4 * sigma * torch.randn(b.shape, generator=gj))
+              for st, (a, b) in lora0.items()}
+        bj = base if frozen_base else make_client_state_dict(base, j, seed, sigma)
+        clients.append(wrap(bj, lj, base["classifier.weight"] + sigma * torch.randn(cfg.n_cls, h, generator=gj),
+                            base["classifier.bias"] + sigma * torch.randn(cfg.n_cls, generator=gj)))
+    return w0, clients
+
+
 def client_sizes(n_clients: int) -> List[int]:
     return [1000 * (j + 1) for j in range(n_clients)]
 
