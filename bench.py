@@ -218,7 +218,8 @@ def parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev):
     coalitions = list(powerset(range(n_c)))
     sv, preds, util = {}, {}, {}
     t0 = time.perf_counter()
-    for prec in (a.precision, "f32"):
+    gate = "f16x3" if a.precision in ("f16", "bf16", "tf32") else None   # the tensor-core mode that meets the top-1 gate
+    for prec in [x for x in (a.precision, gate, "f32") if x]:
         eng = CoalitionEngine(cfg, w0, deltas[:n_c].contiguous(), images, labels, precision=prec, coalition_batch=5,
                               image_chunk=min(32, n_img), device=dev, keep_logits=True)
         clients = [ClientBase(i, {}, None, synth.SizedStub(n)) for i, n in enumerate(n_train)]
@@ -246,10 +247,19 @@ def parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev):
     err = max(abs(x - y) for d in range(2) for x, y in zip(sv[a.precision][d], sv[ref][d]))
     agree = (preds[a.precision] == preds[ref]).float().mean(dim=1)
     du = max(abs(u[0] - v[0]) for u, v in zip(util[a.precision], util[ref]))
-    return {"shapley_abs_err": err, "top1_agreement_min": float(agree.min()), "top1_agreement_mean": float(agree.mean()),
-            "accuracy_utility_abs_err_max": du, "reference": "this library's fp32 mode (held to the CPU oracle in tests/test_gpu_forward.py)",
-            "game": f"{n_c} clients, {len(coalitions)} coalitions, {n_img} images, {a.vit} @ {a.image}px, exact Shapley",
-            "seconds": time.perf_counter() - t0}
+    out = {"shapley_abs_err": err, "top1_agreement_min": float(agree.min()), "top1_agreement_mean": float(agree.mean()),
+           "accuracy_utility_abs_err_max": du, "reference": "this library's fp32 mode (held to the CPU oracle in tests/test_gpu_forward.py)",
+           "game": f"{n_c} clients, {len(coalitions)} coalitions, {n_img} images, {a.vit} @ {a.image}px, exact Shapley"}
+    if gate:
+        ag = (preds[gate] == preds[ref]).float().mean(dim=1)
+        out["gate_mode"] = {
+            "precision": gate, "shapley_abs_err": max(abs(x - y) for d in range(2) for x, y in zip(sv[gate][d], sv[ref][d])),
+            "top1_agreement_min": float(ag.min()), "top1_agreement_mean": float(ag.mean()),
+            "accuracy_utility_abs_err_max": max(abs(u[0] - v[0]) for u, v in zip(util[gate], util[ref])),
+            "note": "split-precision tensor-core mode (fp16 hi/lo operands, 3 MMA passes): `python bench.py --precision f16x3`, "
+                    "measured line in profiles/r1_bench_f16x3.json"}
+    out["seconds"] = time.perf_counter() - t0
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
