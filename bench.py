@@ -58,9 +58,11 @@ def parse_args():
 
 
 def workload_name(a):
+    cfg2 = (a.clients, a.vit, a.image, a.val, a.classes) == (8, "base", 224, 10000, 10)
+    cfg4 = (a.clients, a.vit, a.image, a.coalition_batch) == (10, "large", 224, 32)
+    tag = "BASELINE config 2" if cfg2 else "BASELINE config 4 geometry" if cfg4 else "not a BASELINE configuration"
     return (f"{a.clients}-client FedAvg ViT-{a.vit}/16 @{a.image}px, exact-Shapley enumeration "
-            f"({2 ** a.clients - 1} coalitions), {a.val}-image synthetic val set, {a.classes} classes "
-            f"(BASELINE config 2)")
+            f"({2 ** a.clients - 1} coalitions), {a.val}-image synthetic val set, {a.classes} classes ({tag})")
 
 
 def load_peaks():

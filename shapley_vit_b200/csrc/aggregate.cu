@@ -235,44 +235,72 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
       OutT* outp = reinterpret_cast<OutT*>(p.out) + t * TILE;
 #pragma unroll 1
       for (int ch = 0; ch < nchunks; ++ch) {
+        // 16-bit outputs start from W_0 (one rounding fewer per output and no add in the epilogue; the
+        // value is rounded to 11 / 8 bits right after); fp32 outputs keep the reference's order
+        // W_0 + (sum_j r_j d_j), so their accumulators start from zero
+        constexpr bool kFromW0 = sizeof(OutT) != 4;
         float2 acc[kCChunk][4];
 #pragma unroll
         for (int cc = 0; cc < kCChunk; ++cc)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[cc][q] = make_float2(0.f, 0.f);
+          for (int q = 0; q < 4; ++q) acc[cc][q] = (kFromW0 && !p.base) ? w[q] : make_float2(0.f, 0.f);
         const float4* rt = reinterpret_cast<const float4*>(s_ratio + (size_t)ch * N * kCChunk);
         const uint32_t* mk = s_mask + ch * N;
-        // the loads of client j + 1 (parameters, membership word, ratios) are issued before the
-        // arithmetic of client j, so their shared-memory latency is not on the branch at the loop top
-        float4 da = *reinterpret_cast<const float4*>(st + ea);
-        float4 db = *reinterpret_cast<const float4*>(st + eb);
-        uint32_t m = mk[0];
-        float4 r0 = rt[0], r1 = rt[1];
-#pragma unroll 1
-        for (int j = 0; j < N; ++j) {
-          if (!PF) {
-            da = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + ea);
-            db = *reinterpret_cast<const float4*>(st + (size_t)j * TILE + eb);
-            m = mk[j];
-            r0 = rt[2 * j], r1 = rt[2 * j + 1];
-          }
+        // one client's contribution to the chunk's 8 coalitions
+        auto fold = [&](const float4& da, const float4& db, uint32_t mc, const float4& r0, const float4& r1) {
           const float2 d[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y),
                                make_float2(db.z, db.w)};
-          const uint32_t mc = m;
           const float r[kCChunk] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          if (PF && j + 1 < N) {
-            da = *reinterpret_cast<const float4*>(st + (size_t)(j + 1) * TILE + ea);
-            db = *reinterpret_cast<const float4*>(st + (size_t)(j + 1) * TILE + eb);
-            m = mk[j + 1];
-            r0 = rt[2 * j + 2], r1 = rt[2 * j + 3];
-          }
 #pragma unroll
           for (int cc = 0; cc < kCChunk; ++cc) {
-            if (mc & (1u << cc)) {  // warp-uniform: a real branch skips the 4 packed products and the 8 sums
+            if (mc & (1u << cc)) {  // warp-uniform
 #pragma unroll
               for (int q = 0; q < 4; ++q) acc[cc][q] = accumulate<OutT>(acc[cc][q], r[cc], d[q]);
             }
           }
+        };
+        constexpr int ROW4 = TILE / 4;  // float4 per staged row
+        const float4* pa = reinterpret_cast<const float4*>(st + ea);
+        const float4* pb = reinterpret_cast<const float4*>(st + eb);
+        if (PF) {
+          // two-deep software pipeline, unrolled by two clients so the prefetched registers are used where
+          // they land (no rotation moves): the loads of client j + 1 are in flight during the arithmetic of j
+          float4 da0 = pa[0], db0 = pb[0], r00 = rt[0], r01 = rt[1];
+          uint32_t m0 = mk[0];
+          int rem = N;  // clients left, counting the one already in set 0 (compared with immediates only)
+#pragma unroll 1
+          for (; rem >= 2; rem -= 2) {
+            const float4 da1 = pa[ROW4], db1 = pb[ROW4], r10 = rt[2], r11 = rt[3];
+            const uint32_t m1 = mk[1];
+            fold(da0, db0, m0, r00, r01);
+            pa += 2 * ROW4, pb += 2 * ROW4, rt += 4, mk += 2;
+            if (rem > 2) da0 = pa[0], db0 = pb[0], r00 = rt[0], r01 = rt[1], m0 = mk[0];
+            fold(da1, db1, m1, r10, r11);
+          }
+          if (rem == 1) fold(da0, db0, m0, r00, r01);
+        } else {
+#pragma unroll 1
+          for (int rem = N; rem > 0; --rem) {
+            fold(pa[0], pb[0], mk[0], rt[0], rt[1]);
+            pa += ROW4, pb += ROW4, rt += 2, mk += 1;
+          }
+        }
+        // full tile, shared W_0: every store is a whole vector and the row pointer just advances
+        if (len == TILE && !p.base) {
+          OutT* o = outp + (size_t)ch * kCChunk * p.out_stride;
+          const int ncc = min(kCChunk, C - ch * kCChunk);
+#pragma unroll
+          for (int cc = 0; cc < kCChunk; ++cc) {
+            if (cc < ncc) {
+              float2 v[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v[q] = kFromW0 ? acc[cc][q] : add2(w[q], acc[cc][q]);
+              Store4<OutT>::st(o + ea, v[0], v[1]);
+              Store4<OutT>::st(o + eb, v[2], v[3]);
+              o += p.out_stride;
+            }
+          }
+          continue;
         }
 #pragma unroll
         for (int cc = 0; cc < kCChunk; ++cc) {
@@ -283,7 +311,7 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
             for (int q = 0; q < 4; ++q) wb[q] = w[q];
             if (p.base) load_base(p.base + (size_t)c * p.base_stride + t * TILE_, ea, eb, len, wb);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = add2(wb[q], acc[cc][q]);
+            for (int q = 0; q < 4; ++q) v[q] = (kFromW0 && !p.base) ? acc[cc][q] : add2(wb[q], acc[cc][q]);
             OutT* o = outp + (size_t)c * p.out_stride;
 #pragma unroll
             for (int grp = 0; grp < 2; ++grp) {
