@@ -7,13 +7,15 @@
 // launches per key, each re-reading its operands).
 //
 // Data movement: the stacked deltas [N, P] and W_0 [P] are streamed from HBM exactly once.
-// A persistent CTA owns tiles of TILE consecutive parameters; one elected thread stages the
-// N+1 rows of a tile into shared memory with 1-D TMA bulk copies (cp.async.bulk, completion on
-// an mbarrier), STAGES tiles deep, so the loads in flight do not depend on occupancy or
-// registers.  Each thread owns 2 x 4 consecutive parameters, keeps 8 coalition accumulators
-// (x8 lanes) in registers, walks the clients in ascending order reading its float4 from shared
-// memory, and writes every coalition's row with 64/128-bit streaming stores.  The arithmetic is
-// FMUL2 (packed fp32x2 products) + FADD: three issue slots per two parameters, same rounding.
+// A persistent CTA owns tiles of 1 024 consecutive parameters; one elected thread stages the rows
+// of a tile into shared memory, <= 8 client rows (+ W_0) per transaction set, with 1-D TMA bulk
+// copies (cp.async.bulk, completion on an mbarrier), two stages deep, so the loads in flight do
+// not depend on occupancy or registers and shared memory per CTA does not grow with N.  Each
+// thread owns 2 x 4 consecutive parameters, keeps 8 coalition accumulators (x8 lanes) in
+// registers, walks the clients in ascending order reading its float4 from shared memory, and
+// writes every coalition's row with 64/128-bit streaming stores.  fp32 outputs: FMUL2 (packed
+// fp32x2 products) + FADD, three issue slots per two parameters, the reference's two roundings;
+// 16-bit outputs: one FFMA2 (scalar ratio x packed pair), accumulators started from W_0.
 //
 // Arithmetic (fp32 output): every product and every sum is a separately rounded fp32 operation
 // (__fmul_rn/__fadd_rn; ptxas would otherwise contract to FMA), in ascending client order,
@@ -131,6 +133,7 @@ struct AggParams {
   int64_t out_stride;
   int64_t P;
   int N, C, stages;
+  int group;  // client rows staged per work item (8, or N when all rows of a multi-chunk launch fit: see launch())
   int64_t num_tiles;
   // FedAvg ratios, by value, in [chunk of 8 coalitions][client j][8] order (0 = not a member or
   // padding), and one membership word per (chunk, j): bit cc <=> coalition 8*chunk+cc contains j.
@@ -159,19 +162,39 @@ __device__ __forceinline__ void load_base(const float* row, int ea, int eb, int 
   w[2] = make_float2(f[4], f[5]), w[3] = make_float2(f[6], f[7]);
 }
 
-// dynamic smem: [STAGES][(N+1)][TILE] floats | ratio table | mask table | mbarriers [STAGES]
-// PF: issue the loads of client j + 1 before the arithmetic of client j (pays when the kernel is
-// HBM-bound, C <= 8; costs issue slots when it is instruction-bound, C > 8)
-template <typename OutT, int BLOCK, bool PF>
-__global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant__ AggParams p) {
-  constexpr int TILE = BLOCK * kVec;
-  constexpr int TILE_ = TILE;
+constexpr int kBlock = 128;
+constexpr int kTile = kBlock * kVec;  // 1024 parameters = 4 KB per staged row
+constexpr int kGroup = 8;             // client rows staged per work item (default)
+
+// One kernel for every (N, C).  A persistent CTA walks its tiles; the work of a tile is split into
+// ITEMS, each one TMA transaction set of <= 8 client rows (+ the W_0 row with a tile's first item):
+//   N <= 8 : one item per tile; every chunk of 8 coalitions folds from the same staged rows;
+//   N  > 8 : (chunk, group of 8 clients) items, chunk-major -- the accumulators of a chunk stay in
+//            registers across its groups, the rows are fetched again per chunk (L2 hits: the same
+//            CTA read them microseconds earlier).
+// Shared memory per CTA therefore does not grow with N (2 stages x 9 rows x 4 KB = 72 KB, three
+// CTAs per SM for any N), the barrier traffic is one wait per 8 rows, and the inner loop is the
+// same two-way unrolled, software-pipelined fold for every shape.
+// dynamic smem: [S][rows_per_stage][kTile] floats | ratio table | mask table | mbarriers [S]
+// MULTI = several items per tile (N > rows per item); !MULTI lets the compiler see that g == 0 always,
+// i.e. that the accumulators die at the end of every item.
+template <typename OutT, bool MULTI>
+__global__ void __launch_bounds__(kBlock, 4) aggregate_kernel(const __grid_constant__ AggParams p) {
+  constexpr int TILE = kTile;
+  constexpr int ROW4 = TILE / 4;  // float4 per staged row
+  // 16-bit outputs start their accumulators from W_0 (one rounding fewer per output and no add in the
+  // epilogue; the value is rounded to 11 / 8 bits right after); fp32 outputs keep the reference's
+  // order W_0 + (sum_j r_j d_j), so their accumulators start from zero
+  constexpr bool kFromW0 = sizeof(OutT) != 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int N = p.N, C = p.C, S = p.stages;
-  const int rows = N + 1;  // row N holds W_0
   const int nchunks = (C + kCChunk - 1) / kCChunk;
+  const int gsz = p.group;
+  const int G = MULTI ? (N + gsz - 1) / gsz : 1;
+  const int srows = min(N, gsz) + 1;         // slot srows - 1 holds the W_0 row
+  const int ipt = G == 1 ? 1 : nchunks * G;  // items per tile
   float* stage_base = reinterpret_cast<float*>(smem_raw);
-  float* s_ratio = stage_base + (size_t)S * rows * TILE;
+  float* s_ratio = stage_base + (size_t)S * srows * TILE;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_ratio + (size_t)nchunks * N * kCChunk);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + ((nchunks * N + 1) & ~1));
   const int tid = threadIdx.x;
@@ -180,94 +203,152 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
     for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < nchunks * N * kCChunk; i += BLOCK) s_ratio[i] = p.ratios[i];
-  for (int i = tid; i < nchunks * N; i += BLOCK) s_mask[i] = p.masks[i];
+  for (int i = tid; i < nchunks * N * kCChunk; i += kBlock) s_ratio[i] = p.ratios[i];
+  for (int i = tid; i < nchunks * N; i += kBlock) s_mask[i] = p.masks[i];
   __syncthreads();
 
   const int64_t P = p.P;
   auto tile_len = [&](int64_t t) -> int { return (int)min((int64_t)TILE, P - t * TILE); };
-  // a tile goes through TMA when its length is a multiple of 4 floats (16 B granules)
-  auto issue = [&](int64_t t, int s) {  // thread 0 only
+  // a tile goes through TMA when its length is a multiple of 4 floats (16 B granules); the ragged
+  // last tile (at most one per launch) is staged by all threads in the consumer path
+  auto issue = [&](int64_t t, int sub, int s) {  // thread 0 only
     const int len = tile_len(t);
-    if (len & 3) return;  // ragged last tile: staged by all threads in the consumer path
-    float* dst = stage_base + (size_t)s * rows * TILE;
+    if (len & 3) return;
+    const int g = MULTI ? sub % G : 0, j0 = g * gsz, nj = min(gsz, N - j0);
+    const bool with_w0 = g == 0 && p.w0 != nullptr;
+    float* dst = stage_base + (size_t)s * srows * TILE;
     const uint32_t bytes = (uint32_t)len * 4u;
-    mbar_expect_tx(&bars[s], bytes * (uint32_t)(p.w0 ? rows : N));
-    for (int j = 0; j < N; ++j)
-      bulk_g2s(dst + (size_t)j * TILE, p.deltas + (size_t)j * p.delta_stride + t * TILE, bytes, &bars[s]);
-    if (p.w0) bulk_g2s(dst + (size_t)N * TILE, p.w0 + t * TILE, bytes, &bars[s]);
+    mbar_expect_tx(&bars[s], bytes * (uint32_t)(nj + (with_w0 ? 1 : 0)));
+    for (int j = 0; j < nj; ++j)
+      bulk_g2s(dst + (size_t)j * TILE, p.deltas + (size_t)(j0 + j) * p.delta_stride + t * TILE, bytes, &bars[s]);
+    if (with_w0) bulk_g2s(dst + (size_t)(srows - 1) * TILE, p.w0 + t * TILE, bytes, &bars[s]);
   };
+  // producer cursor (thread 0): the next item of this CTA's sequence that has not been requested yet
+  int64_t pt = blockIdx.x;
+  int psub = 0;
+  auto issue_next = [&](int s) {
+    if (pt >= p.num_tiles) return;
+    issue(pt, psub, s);
+    if (++psub == ipt) psub = 0, pt += gridDim.x;
+  };
+  if (tid == 0)
+    for (int s = 0; s < S; ++s) issue_next(s);
 
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      const int64_t t = blockIdx.x + (int64_t)s * gridDim.x;
-      if (t < p.num_tiles) issue(t, s);
-    }
-  }
-
+  // Each thread owns two groups of 4 consecutive parameters, TILE/2 apart, so that every 128-bit
+  // shared-memory read of a warp is contiguous (conflict-free).
+  const int ea = tid * 4, eb = TILE / 2 + tid * 4;
+  float2 acc[kCChunk][4];
+  float2 w[4];
   int s = 0;
   uint32_t parity = 0;
   for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
     const int len = tile_len(t);
-    float* st = stage_base + (size_t)s * rows * TILE;
-    if (len & 3) {  // ragged tail (at most one tile per launch): guarded scalar staging
-      for (int j = 0; j < rows; ++j) {
-        const float* src = j < N ? p.deltas + (size_t)j * p.delta_stride + t * TILE : (p.w0 ? p.w0 + t * TILE : nullptr);
-        for (int e = tid; e < TILE; e += BLOCK) st[(size_t)j * TILE + e] = (src && e < len) ? src[e] : 0.f;
+    OutT* outp = reinterpret_cast<OutT*>(p.out) + t * TILE;
+
+    // the chunk's coalition rows: W_0 (or the per-coalition base) + acc, converted and stored
+    auto write_chunk = [&](int ch) {
+      if (len == TILE && !p.base) {  // full tile, shared W_0: whole vectors, the row pointer just advances
+        OutT* o = outp + (size_t)ch * kCChunk * p.out_stride;
+        const int ncc = min(kCChunk, C - ch * kCChunk);
+#pragma unroll
+        for (int cc = 0; cc < kCChunk; ++cc) {
+          if (cc < ncc) {
+            float2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[q] = kFromW0 ? acc[cc][q] : add2(w[q], acc[cc][q]);
+            Store4<OutT>::st(o + ea, v[0], v[1]);
+            Store4<OutT>::st(o + eb, v[2], v[3]);
+            o += p.out_stride;
+          }
+        }
+        return;
       }
-      __syncthreads();
-    } else {
-      mbar_wait(&bars[s], parity);
-    }
-    // Each thread owns two groups of 4 consecutive parameters, TILE/2 apart, so that every
-    // 128-bit shared-memory read of a warp is contiguous (conflict-free).
-    const int ea = tid * 4, eb = TILE / 2 + tid * 4;
-    if (ea < len) {
-      float2 w[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = make_float2(0.f, 0.f);
-      if (p.w0) {
-        const float4 a = *reinterpret_cast<const float4*>(st + (size_t)N * TILE + ea);
-        const float4 b = *reinterpret_cast<const float4*>(st + (size_t)N * TILE + eb);
-        w[0] = make_float2(a.x, a.y), w[1] = make_float2(a.z, a.w);
-        w[2] = make_float2(b.x, b.y), w[3] = make_float2(b.z, b.w);
-      }
-      OutT* outp = reinterpret_cast<OutT*>(p.out) + t * TILE;
-#pragma unroll 1
-      for (int ch = 0; ch < nchunks; ++ch) {
-        // 16-bit outputs start from W_0 (one rounding fewer per output and no add in the epilogue; the
-        // value is rounded to 11 / 8 bits right after); fp32 outputs keep the reference's order
-        // W_0 + (sum_j r_j d_j), so their accumulators start from zero
-        constexpr bool kFromW0 = sizeof(OutT) != 4;
-        float2 acc[kCChunk][4];
+      for (int cc = 0; cc < kCChunk; ++cc) {
+        const int c = ch * kCChunk + cc;
+        if (c < C) {
+          float2 v[4], wb[4];
 #pragma unroll
-        for (int cc = 0; cc < kCChunk; ++cc)
+          for (int q = 0; q < 4; ++q) wb[q] = w[q];
+          if (p.base) load_base(p.base + (size_t)c * p.base_stride + t * TILE, ea, eb, len, wb);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) acc[cc][q] = (kFromW0 && !p.base) ? w[q] : make_float2(0.f, 0.f);
-        const float4* rt = reinterpret_cast<const float4*>(s_ratio + (size_t)ch * N * kCChunk);
-        const uint32_t* mk = s_mask + ch * N;
-        // one client's contribution to the chunk's 8 coalitions
-        auto fold = [&](const float4& da, const float4& db, uint32_t mc, const float4& r0, const float4& r1) {
-          const float2 d[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y),
-                               make_float2(db.z, db.w)};
-          const float r[kCChunk] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          for (int q = 0; q < 4; ++q) v[q] = (kFromW0 && !p.base) ? acc[cc][q] : add2(wb[q], acc[cc][q]);
+          OutT* o = outp + (size_t)c * p.out_stride;
 #pragma unroll
-          for (int cc = 0; cc < kCChunk; ++cc) {
-            if (mc & (1u << cc)) {  // warp-uniform
+          for (int grp = 0; grp < 2; ++grp) {
+            const int e = grp ? eb : ea;
+            if (e + 4 <= len) {
+              Store4<OutT>::st(o + e, v[2 * grp], v[2 * grp + 1]);
+            } else {  // ragged tail: element-wise
+              const float f[4] = {v[2 * grp].x, v[2 * grp].y, v[2 * grp + 1].x, v[2 * grp + 1].y};
 #pragma unroll
-              for (int q = 0; q < 4; ++q) acc[cc][q] = accumulate<OutT>(acc[cc][q], r[cc], d[q]);
+              for (int q = 0; q < 4; ++q)
+                if (e + q < len) o[e + q] = Cvt<OutT>::from_f(f[q]);
             }
           }
-        };
-        constexpr int ROW4 = TILE / 4;  // float4 per staged row
-        const float4* pa = reinterpret_cast<const float4*>(st + ea);
-        const float4* pb = reinterpret_cast<const float4*>(st + eb);
-        if (PF) {
+        }
+      }
+    };
+
+    for (int sub = 0; sub < ipt; ++sub) {
+      const int g = MULTI ? sub % G : 0, ch0 = MULTI ? sub / G : 0;  // (G == 1: the chunk loop runs below)
+      const int j0 = g * gsz, nj = min(gsz, N - j0);
+      float* st = stage_base + (size_t)s * srows * TILE;
+      if (len & 3) {  // ragged tail: guarded scalar staging of this item's rows
+        for (int j = 0; j <= nj; ++j) {
+          const float* src = j < nj ? p.deltas + (size_t)(j0 + j) * p.delta_stride + t * TILE
+                                    : ((g == 0 && p.w0) ? p.w0 + t * TILE : nullptr);
+          float* dst = st + (size_t)(j < nj ? j : srows - 1) * TILE;
+          if (j == nj && g != 0) break;
+          for (int e = tid; e < TILE; e += kBlock) dst[e] = (src && e < len) ? src[e] : 0.f;
+        }
+        __syncthreads();
+      } else {
+        mbar_wait(&bars[s], parity);
+      }
+      if (ea < len) {
+        if (g == 0) {  // first item of a tile (G == 1) or of a (tile, chunk): W_0 arrives with it
+#pragma unroll
+          for (int q = 0; q < 4; ++q) w[q] = make_float2(0.f, 0.f);
+          if (p.w0) {
+            const float4 a = *reinterpret_cast<const float4*>(st + (size_t)(srows - 1) * TILE + ea);
+            const float4 b = *reinterpret_cast<const float4*>(st + (size_t)(srows - 1) * TILE + eb);
+            w[0] = make_float2(a.x, a.y), w[1] = make_float2(a.z, a.w);
+            w[2] = make_float2(b.x, b.y), w[3] = make_float2(b.z, b.w);
+          }
+        }
+        const int nch = G == 1 ? nchunks : 1;  // chunks folded from this item's rows
+#pragma unroll 1
+        for (int k = 0; k < nch; ++k) {
+          const int ch = G == 1 ? k : ch0;
+          if (g == 0) {
+#pragma unroll
+            for (int cc = 0; cc < kCChunk; ++cc)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) acc[cc][q] = (kFromW0 && !p.base) ? w[q] : make_float2(0.f, 0.f);
+          }
+          const float4* rt = reinterpret_cast<const float4*>(s_ratio + ((size_t)ch * N + j0) * kCChunk);
+          const uint32_t* mk = s_mask + ch * N + j0;
+          // one client's contribution to the chunk's 8 coalitions
+          auto fold = [&](const float4& da, const float4& db, uint32_t mc, const float4& r0, const float4& r1) {
+            const float2 d[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y),
+                                 make_float2(db.z, db.w)};
+            const float r[kCChunk] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int cc = 0; cc < kCChunk; ++cc) {
+              if (mc & (1u << cc)) {  // warp-uniform
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[cc][q] = accumulate<OutT>(acc[cc][q], r[cc], d[q]);
+              }
+            }
+          };
+          const float4* pa = reinterpret_cast<const float4*>(st + ea);
+          const float4* pb = reinterpret_cast<const float4*>(st + eb);
           // two-deep software pipeline, unrolled by two clients so the prefetched registers are used where
           // they land (no rotation moves): the loads of client j + 1 are in flight during the arithmetic of j
           float4 da0 = pa[0], db0 = pb[0], r00 = rt[0], r01 = rt[1];
           uint32_t m0 = mk[0];
-          int rem = N;  // clients left, counting the one already in set 0 (compared with immediates only)
+          int rem = nj;  // clients left, counting the one already in set 0 (compared with immediates only)
 #pragma unroll 1
           for (; rem >= 2; rem -= 2) {
             const float4 da1 = pa[ROW4], db1 = pb[ROW4], r10 = rt[2], r11 = rt[3];
@@ -278,301 +359,55 @@ __global__ void __launch_bounds__(BLOCK) aggregate_kernel(const __grid_constant_
             fold(da1, db1, m1, r10, r11);
           }
           if (rem == 1) fold(da0, db0, m0, r00, r01);
-        } else {
-#pragma unroll 1
-          for (int rem = N; rem > 0; --rem) {
-            fold(pa[0], pb[0], mk[0], rt[0], rt[1]);
-            pa += ROW4, pb += ROW4, rt += 2, mk += 1;
-          }
-        }
-        // full tile, shared W_0: every store is a whole vector and the row pointer just advances
-        if (len == TILE && !p.base) {
-          OutT* o = outp + (size_t)ch * kCChunk * p.out_stride;
-          const int ncc = min(kCChunk, C - ch * kCChunk);
-#pragma unroll
-          for (int cc = 0; cc < kCChunk; ++cc) {
-            if (cc < ncc) {
-              float2 v[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) v[q] = kFromW0 ? acc[cc][q] : add2(w[q], acc[cc][q]);
-              Store4<OutT>::st(o + ea, v[0], v[1]);
-              Store4<OutT>::st(o + eb, v[2], v[3]);
-              o += p.out_stride;
-            }
-          }
-          continue;
-        }
-#pragma unroll
-        for (int cc = 0; cc < kCChunk; ++cc) {
-          const int c = ch * kCChunk + cc;
-          if (c < C) {
-            float2 v[4], wb[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) wb[q] = w[q];
-            if (p.base) load_base(p.base + (size_t)c * p.base_stride + t * TILE_, ea, eb, len, wb);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = (kFromW0 && !p.base) ? acc[cc][q] : add2(wb[q], acc[cc][q]);
-            OutT* o = outp + (size_t)c * p.out_stride;
-#pragma unroll
-            for (int grp = 0; grp < 2; ++grp) {
-              const int e = grp ? eb : ea;
-              if (e + 4 <= len) {
-                Store4<OutT>::st(o + e, v[2 * grp], v[2 * grp + 1]);
-              } else {  // ragged tail: element-wise
-                const float f[4] = {v[2 * grp].x, v[2 * grp].y, v[2 * grp + 1].x, v[2 * grp + 1].y};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  if (e + q < len) o[e + q] = Cvt<OutT>::from_f(f[q]);
-              }
-            }
-          }
+          if (g == G - 1) write_chunk(ch);
         }
       }
-    }
-    __syncthreads();  // everyone is done reading stage s
-    if (tid == 0) {
-      const int64_t tn = t + (int64_t)S * gridDim.x;
-      if (tn < p.num_tiles) issue(tn, s);
-    }
-    if (++s == S) {
-      s = 0;
-      parity ^= 1;
+      __syncthreads();  // everyone is done reading stage s
+      if (tid == 0) issue_next(s);
+      if (++s == S) {
+        s = 0;
+        parity ^= 1;
+      }
     }
   }
 }
 
-template <typename OutT, int BLOCK, bool PF>
+template <typename OutT>
 int launch(const AggParams& base, cudaStream_t stream) {
   AggParams p = base;
-  constexpr int TILE = BLOCK * kVec;
-  p.num_tiles = (p.P + TILE - 1) / TILE;
+  p.num_tiles = (p.P + kTile - 1) / kTile;
   const int nchunks = (p.C + kCChunk - 1) / kCChunk;
-  const size_t stage_bytes = (size_t)(p.N + 1) * TILE * 4;
+  // Rows per item: 8.  With several chunks of coalitions AND more than 8 clients the rows would be
+  // fetched once per chunk; up to N = 13 the whole tile (N + 1 rows, two stages, two CTAs per SM) still
+  // fits, every chunk folds from the same staged rows and nothing is fetched twice.
+  p.group = (nchunks > 1 && p.N > kGroup && p.N <= 13) ? p.N : kGroup;
+  const int srows = (p.N < p.group ? p.N : p.group) + 1;
+  const size_t stage_bytes = (size_t)srows * kTile * 4;
   const size_t fixed = (size_t)nchunks * p.N * kCChunk * 4 + (size_t)((nchunks * p.N + 1) & ~1) * 4 + 8 * 8;
   const size_t budget = 227 * 1024;
   // Two stages per CTA and as many CTAs per SM as fit: the loads in flight per SM are the same as
-  // with deeper rings, but more warps hide the shared-memory and branch latency of the inner loop.
+  // with deeper rings, but more warps hide the shared-memory latency of the inner loop.
   int stages = 2;
-  if (stages * stage_bytes + fixed > budget)
-    SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "svit_aggregate: N=%d does not fit shared memory", p.N);
   if (4 * stage_bytes + fixed + 1024 <= budget / 3) stages = 4;
   else if (3 * stage_bytes + fixed + 1024 <= budget / 3) stages = 3;
   p.stages = stages;
   const size_t smem = stages * stage_bytes + fixed;
-  int per_sm = (int)(budget / (smem + 1024));  // +1 KB per-CTA reservation
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 8) per_sm = 8;
-  auto kern = aggregate_kernel<OutT, BLOCK, PF>;
+  if (smem > budget) SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "svit_aggregate: ratio tables of N=%d, C=%d do not fit shared memory", p.N, p.C);
+  auto kern = p.N > p.group ? aggregate_kernel<OutT, true> : aggregate_kernel<OutT, false>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;  // resident CTAs per SM (registers and shared memory): the grid is exactly one wave
+  SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+  if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  kern<<<(unsigned)grid, BLOCK, smem, stream>>>(p);
+  kern<<<(unsigned)grid, kBlock, smem, stream>>>(p);
   SVIT_LAUNCH_CHECK("aggregate_kernel");
-  return SVIT_OK;
-}
-
-
-// ---- row-ring variant -------------------------------------------------------------------------
-// Same arithmetic, different staging: instead of holding all N+1 rows of a tile in shared memory
-// (whose footprint grows with N and costs occupancy: 0.50 of the copy peak at N = 16, 0.13 at
-// N = 64), a producer warp streams ONE 4 KB row-tile at a time through a ring of kRingSlots slots
-// and four consumer warps fold each row into their 8 coalition accumulators as it lands.  Shared
-// memory per CTA is independent of N.  For C > 8 the rows of a tile are streamed once per chunk of
-// 8 coalitions (the re-reads hit L2: the tile's rows were read a few microseconds earlier), and a
-// row none of the chunk's coalitions contains is not fetched at all.
-constexpr int kRingSlots = 8;
-constexpr int kRingConsumers = 128;                  // 4 warps x 8 parameters per thread
-constexpr int kRingTile = kRingConsumers * kVec;     // 1024 parameters = 4 KB per row-tile
-constexpr int kRingThreads = kRingConsumers + 32;    // + the producer warp
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// dynamic smem: [kRingSlots][kRingTile] floats | ratio table | mask table | full[kRingSlots] | empty[kRingSlots]
-template <typename OutT>
-__global__ void __launch_bounds__(kRingThreads) aggregate_ring_kernel(const __grid_constant__ AggParams p) {
-  constexpr int TILE_ = kRingTile;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int N = p.N, C = p.C;
-  const int nchunks = (C + kCChunk - 1) / kCChunk;
-  float* ring = reinterpret_cast<float*>(smem_raw);
-  float* s_ratio = ring + (size_t)kRingSlots * kRingTile;
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_ratio + (size_t)nchunks * N * kCChunk);
-  uint64_t* full = reinterpret_cast<uint64_t*>(s_mask + ((nchunks * N + 1) & ~1));
-  uint64_t* empty = full + kRingSlots;
-  const int tid = threadIdx.x;
-
-  if (tid == 0) {
-    for (int s = 0; s < kRingSlots; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kRingConsumers / 32);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < nchunks * N * kCChunk; i += kRingThreads) s_ratio[i] = p.ratios[i];
-  for (int i = tid; i < nchunks * N; i += kRingThreads) s_mask[i] = p.masks[i];
-  __syncthreads();
-
-  const int64_t P = p.P;
-  const bool has_w0 = p.w0 != nullptr;
-  // Producer and consumers walk the same sequence: for tile, for chunk, for each row with a member in
-  // the chunk (ascending j), then the W_0 row.  A tile whose length is not a multiple of 4 floats (at
-  // most the last one) bypasses the ring: the consumers read it with guarded scalar loads.
-  if (tid >= kRingConsumers) {  // ===== producer warp =====
-    if (tid == kRingConsumers) {
-      uint32_t seq = 0;
-      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int len = (int)min((int64_t)kRingTile, P - t * kRingTile);
-        if (len & 3) continue;
-        const uint32_t bytes = (uint32_t)len * 4u;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          for (int j = 0; j <= N; ++j) {
-            const float* src;
-            if (j < N) {
-              if (s_mask[ch * N + j] == 0) continue;
-              src = p.deltas + (size_t)j * p.delta_stride + t * kRingTile;
-            } else {
-              if (!has_w0) continue;
-              src = p.w0 + t * kRingTile;
-            }
-            const uint32_t s = seq % kRingSlots;
-            mbar_wait(&empty[s], ((seq / kRingSlots) & 1) ^ 1);
-            mbar_expect_tx(&full[s], bytes);
-            bulk_g2s(ring + (size_t)s * kRingTile, src, bytes, &full[s]);
-            ++seq;
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumers =====
-  const int lane = tid & 31;
-  const int ea = tid * 4, eb = kRingTile / 2 + tid * 4;  // two float4 per thread, each warp access contiguous
-  uint32_t seq = 0;
-  for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-    const int len = (int)min((int64_t)kRingTile, P - t * kRingTile);
-    const bool ragged = (len & 3) != 0;
-    OutT* outp = reinterpret_cast<OutT*>(p.out) + t * kRingTile;
-#pragma unroll 1
-    for (int ch = 0; ch < nchunks; ++ch) {
-      float2 acc[kCChunk][4];
-#pragma unroll
-      for (int cc = 0; cc < kCChunk; ++cc)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[cc][q] = make_float2(0.f, 0.f);
-      float2 w[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-      const float4* rt = reinterpret_cast<const float4*>(s_ratio + (size_t)ch * N * kCChunk);
-      const uint32_t* mk = s_mask + ch * N;
-#pragma unroll 1
-      for (int j = 0; j <= N; ++j) {
-        uint32_t m = 0;
-        const float* grow;
-        if (j < N) {
-          m = mk[j];
-          if (m == 0) continue;
-          grow = p.deltas + (size_t)j * p.delta_stride + t * kRingTile;
-        } else {
-          if (!has_w0) continue;
-          grow = p.w0 + t * kRingTile;
-        }
-        float4 da, db;
-        if (!ragged) {
-          const uint32_t s = seq % kRingSlots;
-          mbar_wait(&full[s], (seq / kRingSlots) & 1);
-          const float* st = ring + (size_t)s * kRingTile;
-          da = *reinterpret_cast<const float4*>(st + ea);
-          db = *reinterpret_cast<const float4*>(st + eb);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);  // this warp has its copy of the slot in registers
-          ++seq;
-        } else {
-          float f[8];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            f[q] = ea + q < len ? grow[ea + q] : 0.f;
-            f[4 + q] = eb + q < len ? grow[eb + q] : 0.f;
-          }
-          da = make_float4(f[0], f[1], f[2], f[3]);
-          db = make_float4(f[4], f[5], f[6], f[7]);
-        }
-        const float2 d[4] = {make_float2(da.x, da.y), make_float2(da.z, da.w), make_float2(db.x, db.y),
-                             make_float2(db.z, db.w)};
-        if (j == N) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) w[q] = d[q];
-        } else {
-          const float4 r0 = rt[2 * j], r1 = rt[2 * j + 1];
-          const float r[kCChunk] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-          for (int cc = 0; cc < kCChunk; ++cc) {
-            if (m & (1u << cc)) {  // warp-uniform: a real branch skips the packed products and the sums
-#pragma unroll
-              for (int q = 0; q < 4; ++q) acc[cc][q] = accumulate<OutT>(acc[cc][q], r[cc], d[q]);
-            }
-          }
-        }
-      }
-      if (ea < len) {
-#pragma unroll
-        for (int cc = 0; cc < kCChunk; ++cc) {
-          const int c = ch * kCChunk + cc;
-          if (c < C) {
-            float2 v[4], wb[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) wb[q] = w[q];
-            if (p.base) load_base(p.base + (size_t)c * p.base_stride + t * TILE_, ea, eb, len, wb);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = add2(wb[q], acc[cc][q]);
-            OutT* o = outp + (size_t)c * p.out_stride;
-#pragma unroll
-            for (int grp = 0; grp < 2; ++grp) {
-              const int e = grp ? eb : ea;
-              if (e + 4 <= len) {
-                Store4<OutT>::st(o + e, v[2 * grp], v[2 * grp + 1]);
-              } else {  // ragged tail: element-wise
-                const float f[4] = {v[2 * grp].x, v[2 * grp].y, v[2 * grp + 1].x, v[2 * grp + 1].y};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  if (e + q < len) o[e + q] = Cvt<OutT>::from_f(f[q]);
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-}
-
-template <typename OutT>
-int launch_ring(const AggParams& base, cudaStream_t stream) {
-  AggParams p = base;
-  p.num_tiles = (p.P + kRingTile - 1) / kRingTile;
-  const int nchunks = (p.C + kCChunk - 1) / kCChunk;
-  const size_t smem = (size_t)kRingSlots * kRingTile * 4 + (size_t)nchunks * p.N * kCChunk * 4 +
-                      (size_t)((nchunks * p.N + 1) & ~1) * 4 + 2 * kRingSlots * 8;
-  auto kern = aggregate_ring_kernel<OutT>;
-  SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRingThreads, smem));
-  if (per_sm < 1) per_sm = 1;
-  int64_t grid = (int64_t)sm_count() * per_sm;
-  if (grid > p.num_tiles) grid = p.num_tiles;
-  kern<<<(unsigned)grid, kRingThreads, smem, stream>>>(p);
-  SVIT_LAUNCH_CHECK("aggregate_ring_kernel");
   return SVIT_OK;
 }
 
 template <typename OutT>
 int dispatch_block(const AggParams& p, cudaStream_t stream) {
-  static const int mode = [] { const char* e = getenv("SVIT_AGG_RING"); return e ? atoi(e) : -1; }();  // -1 auto, 0 never, 1 always
-  // measured (scripts/microbench.py agg): the ring wins whenever staging N+1 rows per tile costs occupancy
-  if (mode == 1 || (mode < 0 && p.N > 8 && (p.C <= 8 || p.N >= 16))) return launch_ring<OutT>(p, stream);
-  if (p.N <= 17) return p.C <= 8 ? launch<OutT, 128, true>(p, stream) : launch<OutT, 128, false>(p, stream);
-  if (p.N <= 35) return launch<OutT, 64, false>(p, stream);
-  return launch<OutT, 32, false>(p, stream);
+  return launch<OutT>(p, stream);
 }
 
 }  // namespace

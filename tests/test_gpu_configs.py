@@ -39,7 +39,7 @@ def _games(n_clients, n_val, prec):
 
 
 def test_cfg3_sixteen_clients_monte_carlo_and_gtg_truncation():
-    """16 clients (K1 takes the row-ring kernel), fp32 mode: identical permutation streams, identical utilities
+    """16 clients (K1 walks two groups of 8 client rows per tile), fp32 mode: identical permutation streams, identical utilities
     (integer correct counts), hence identical Shapley vectors up to fp32 loss noise."""
     gpu, ora = _games(16, 64, "f32")
     sv = []
