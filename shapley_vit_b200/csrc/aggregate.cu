@@ -165,6 +165,13 @@ __device__ __forceinline__ void load_base(const float* row, int ea, int eb, int 
 constexpr int kBlock = 128;
 constexpr int kTile = kBlock * kVec;  // 1024 parameters = 4 KB per staged row
 constexpr int kGroup = 8;             // client rows staged per work item (default)
+constexpr int kThreads = kBlock + 32;  // four consumer warps + the producer warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the 128 consumer threads only (the producer warp never joins): ragged-tile staging
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // One kernel for every (N, C).  A persistent CTA walks its tiles; the work of a tile is split into
 // ITEMS, each one TMA transaction set of <= 8 client rows (+ the W_0 row with a tile's first item):
@@ -179,7 +186,7 @@ constexpr int kGroup = 8;             // client rows staged per work item (defau
 // MULTI = several items per tile (N > rows per item); !MULTI lets the compiler see that g == 0 always,
 // i.e. that the accumulators die at the end of every item.
 template <typename OutT, bool MULTI>
-__global__ void __launch_bounds__(kBlock, 4) aggregate_kernel(const __grid_constant__ AggParams p) {
+__global__ void __launch_bounds__(kThreads, 3) aggregate_kernel(const __grid_constant__ AggParams p) {
   constexpr int TILE = kTile;
   constexpr int ROW4 = TILE / 4;  // float4 per staged row
   // 16-bit outputs start their accumulators from W_0 (one rounding fewer per output and no add in the
@@ -196,15 +203,19 @@ __global__ void __launch_bounds__(kBlock, 4) aggregate_kernel(const __grid_const
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   float* s_ratio = stage_base + (size_t)S * srows * TILE;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_ratio + (size_t)nchunks * N * kCChunk);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + ((nchunks * N + 1) & ~1));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + ((nchunks * N + 1) & ~1));  // full[S]
+  uint64_t* empty = bars + S;
   const int tid = threadIdx.x;
 
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&bars[s], 1);
+      mbar_init(&empty[s], kBlock / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < nchunks * N * kCChunk; i += kBlock) s_ratio[i] = p.ratios[i];
-  for (int i = tid; i < nchunks * N; i += kBlock) s_mask[i] = p.masks[i];
+  for (int i = tid; i < nchunks * N * kCChunk; i += kThreads) s_ratio[i] = p.ratios[i];
+  for (int i = tid; i < nchunks * N; i += kThreads) s_mask[i] = p.masks[i];
   __syncthreads();
 
   const int64_t P = p.P;
@@ -223,16 +234,20 @@ __global__ void __launch_bounds__(kBlock, 4) aggregate_kernel(const __grid_const
       bulk_g2s(dst + (size_t)j * TILE, p.deltas + (size_t)(j0 + j) * p.delta_stride + t * TILE, bytes, &bars[s]);
     if (with_w0) bulk_g2s(dst + (size_t)(srows - 1) * TILE, p.w0 + t * TILE, bytes, &bars[s]);
   };
-  // producer cursor (thread 0): the next item of this CTA's sequence that has not been requested yet
-  int64_t pt = blockIdx.x;
-  int psub = 0;
-  auto issue_next = [&](int s) {
-    if (pt >= p.num_tiles) return;
-    issue(pt, psub, s);
-    if (++psub == ipt) psub = 0, pt += gridDim.x;
-  };
-  if (tid == 0)
-    for (int s = 0; s < S; ++s) issue_next(s);
+  // ===== producer warp: walks the same item sequence as the consumers, one stage ahead of their releases =====
+  if (tid >= kBlock) {
+    if (tid == kBlock) {
+      int ps_ = 0;
+      uint32_t pph = 0;
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x)
+        for (int sub = 0; sub < ipt; ++sub) {
+          mbar_wait(&empty[ps_], pph ^ 1);  // all four consumer warps have released the stage (free at start)
+          issue(t, sub, ps_);
+          if (++ps_ == S) ps_ = 0, pph ^= 1;
+        }
+    }
+    return;
+  }
 
   // Each thread owns two groups of 4 consecutive parameters, TILE/2 apart, so that every 128-bit
   // shared-memory read of a warp is contiguous (conflict-free).
@@ -295,6 +310,7 @@ __global__ void __launch_bounds__(kBlock, 4) aggregate_kernel(const __grid_const
       const int j0 = g * gsz, nj = min(gsz, N - j0);
       float* st = stage_base + (size_t)s * srows * TILE;
       if (len & 3) {  // ragged tail: guarded scalar staging of this item's rows
+        consumer_sync();  // nobody still reads an earlier item from this stage
         for (int j = 0; j <= nj; ++j) {
           const float* src = j < nj ? p.deltas + (size_t)(j0 + j) * p.delta_stride + t * TILE
                                     : ((g == 0 && p.w0) ? p.w0 + t * TILE : nullptr);
@@ -302,7 +318,7 @@ __global__ void __launch_bounds__(kBlock, 4) aggregate_kernel(const __grid_const
           if (j == nj && g != 0) break;
           for (int e = tid; e < TILE; e += kBlock) dst[e] = (src && e < len) ? src[e] : 0.f;
         }
-        __syncthreads();
+        consumer_sync();
       } else {
         mbar_wait(&bars[s], parity);
       }
@@ -362,8 +378,8 @@ __global__ void __launch_bounds__(kBlock, 4) aggregate_kernel(const __grid_const
           if (g == G - 1) write_chunk(ch);
         }
       }
-      __syncthreads();  // everyone is done reading stage s
-      if (tid == 0) issue_next(s);
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done reading stage s
       if (++s == S) {
         s = 0;
         parity ^= 1;
@@ -383,7 +399,7 @@ int launch(const AggParams& base, cudaStream_t stream) {
   p.group = (nchunks > 1 && p.N > kGroup && p.N <= 13) ? p.N : kGroup;
   const int srows = (p.N < p.group ? p.N : p.group) + 1;
   const size_t stage_bytes = (size_t)srows * kTile * 4;
-  const size_t fixed = (size_t)nchunks * p.N * kCChunk * 4 + (size_t)((nchunks * p.N + 1) & ~1) * 4 + 8 * 8;
+  const size_t fixed = (size_t)nchunks * p.N * kCChunk * 4 + (size_t)((nchunks * p.N + 1) & ~1) * 4 + 2 * 8 * 8;
   const size_t budget = 227 * 1024;
   // Two stages per CTA and as many CTAs per SM as fit: the loads in flight per SM are the same as
   // with deeper rings, but more warps hide the shared-memory latency of the inner loop.
@@ -396,17 +412,20 @@ int launch(const AggParams& base, cudaStream_t stream) {
   auto kern = p.N > p.group ? aggregate_kernel<OutT, true> : aggregate_kernel<OutT, false>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;  // resident CTAs per SM (registers and shared memory): the grid is exactly one wave
-  SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBlock, smem));
+  SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
   int64_t grid = (int64_t)sm_count() * per_sm;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  kern<<<(unsigned)grid, kBlock, smem, stream>>>(p);
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(p);
   SVIT_LAUNCH_CHECK("aggregate_kernel");
   return SVIT_OK;
 }
 
 template <typename OutT>
 int dispatch_block(const AggParams& p, cudaStream_t stream) {
+  // (a variant with 4 or 2 parameters and 16 or 32 coalitions per thread -- half / a quarter of the passes
+  // over a tile's rows when N > 8 and C > 8 -- was measured slower everywhere once the producer warp had
+  // removed the per-item block barrier: 0.45 vs 0.60 of the copy peak at N = 16, C = 32)
   return launch<OutT>(p, stream);
 }
 

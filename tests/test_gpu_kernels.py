@@ -46,7 +46,9 @@ def fedavg_rows(masks, n_train):
 
 
 @pytest.mark.parametrize("N,C,P", [(1, 1, 8), (4, 15, 4096), (8, 32, 100_000), (8, 33, 33_333), (3, 5, 1027),
-                                   (16, 17, 70_001), (20, 9, 5_000), (40, 7, 3_000), (64, 3, 2_049)])
+                                   (16, 17, 70_001), (20, 9, 5_000), (40, 7, 3_000), (64, 3, 2_049),
+                                   # several groups of client rows AND several chunks of coalitions per tile
+                                   (32, 16, 40_003), (16, 33, 9_001), (64, 70, 2_600), (14, 9, 511)])
 def test_aggregate_fp32_bit_exact(ops, N, C, P):
     rng = np.random.RandomState(N * 1000 + C)
     stride = (P + 7) // 8 * 8
@@ -74,9 +76,10 @@ def test_aggregate_no_w0_and_identity(ops):
     assert torch.count_nonzero(got[2]) == 0                     # empty coalition: W0 (= 0) alone
 
 
+@pytest.mark.parametrize("N,C", [(8, 12), (16, 8), (11, 17), (16, 12), (24, 40)])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_aggregate_16bit_is_rounded_fp32_result(ops, dtype):
-    N, C, P = 8, 12, 50_000
+def test_aggregate_16bit_is_rounded_fp32_result(ops, dtype, N, C):
+    P = 50_000
     deltas, w0 = gen(N, P, seed=5) * 0.02, gen(P, seed=6) * 0.02
     rng = np.random.RandomState(0)
     rows = fedavg_rows([rng.rand(N) < 0.6 for _ in range(C - 1)] + [np.ones(N, bool)], list(range(1, N + 1)))
