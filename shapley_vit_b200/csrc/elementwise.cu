@@ -3,6 +3,8 @@
 // Linear).  They restate, per coalition group g, what HF's modeling_vit.py does in
 // embeddings :100-128, layernorm_before/after :325-326, final layernorm :416 and the
 // classifier :641-642 for the model the reference evaluates (federated_learning/utils.py:886).
+#include <cstdlib>
+
 #include "elementwise.h"
 
 namespace svit {
@@ -74,6 +76,52 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       store4<T>(yr + idx * 4, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
                 (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
     }
+  }
+}
+
+// Same arithmetic, in the same order, for the hidden sizes that fill whole warps (h = 128 * VPL: 768, 1024):
+// persistent warps (one resident wave), no bounds predicates, the (coalition, row) pair advanced
+// incrementally instead of by a 64-bit division per row.  Fewer instructions per row than the generic
+// kernel -- which matters inside a forward step, where the GEMMs hold the SM clock at the power cap and
+// this kernel's issue rate, not HBM, paces it.
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) layernorm_fixed_kernel(const float* __restrict__ x, int64_t x_gs, int64_t x_ld,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int64_t param_gs,
+                                                              T* __restrict__ y, int64_t y_gs, int64_t y_ld, int64_t rows,
+                                                              int64_t total_rows, float eps) {
+  constexpr int H = VPL * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t g = r / rows, rr = r - g * rows;
+  for (; r < total_rows; r += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + g * x_gs + rr * x_ld) + lane;
+    float4 v[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) v[i] = xr[i * 32];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(sum) / (float)H;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)H + eps);
+    const float4* gm = reinterpret_cast<const float4*>(gamma + g * param_gs) + lane;  // L1 hits: shared by the coalition's rows
+    const float4* bt = reinterpret_cast<const float4*>(beta + g * param_gs) + lane;
+    T* yr = y + g * y_gs + rr * y_ld + lane * 4;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 gg = gm[i * 32], bb = bt[i * 32];
+      store4<T>(yr + i * 128, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+                (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+    }
+    rr += nwarps;
+    while (rr >= rows) rr -= rows, ++g;
   }
 }
 
@@ -215,6 +263,39 @@ int layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, co
   const int64_t total = (int64_t)G * rows;
   if (total == 0) return SVIT_OK;
   const int wpb = 8;
+  static const bool generic_only = [] {  // SVIT_LN_GENERIC=1: the bounds-checked kernel for every h (A/B)
+    const char* e = getenv("SVIT_LN_GENERIC");
+    return e && e[0] == '1';
+  }();
+  if ((h == 768 || h == 1024) && !generic_only) {  // whole warps: the persistent fixed-size kernel
+    int per_sm = 0;  // one resident wave of persistent warps
+    if (h == 768) {
+      SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_fixed_kernel<__half, 6>, wpb * 32, 0));
+    } else {
+      SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_fixed_kernel<float, 8>, wpb * 32, 0));
+    }
+    if (per_sm < 1) per_sm = 1;
+    const unsigned pgrid = (unsigned)std::min<int64_t>((total + wpb - 1) / wpb, (int64_t)sm_count() * per_sm);
+#define SVIT_LNF(T, V)                                                                                                 \
+  layernorm_fixed_kernel<T, V><<<pgrid, wpb * 32, 0, stream>>>(x, x_gs, x_ld, gamma, beta, param_gs, (T*)y, y_gs, y_ld, \
+                                                               rows, total, eps)
+#define SVIT_LNH(T)          \
+  if (h == 768) {            \
+    SVIT_LNF(T, 6);          \
+  } else {                   \
+    SVIT_LNF(T, 8);          \
+  }
+    switch (out_dtype) {
+      case SVIT_F32: SVIT_LNH(float); break;
+      case SVIT_BF16: SVIT_LNH(__nv_bfloat16); break;
+      case SVIT_F16: SVIT_LNH(__half); break;
+      default: SVIT_FAIL(SVIT_ERR_ARG, "layernorm: bad dtype %d", out_dtype);
+    }
+#undef SVIT_LNH
+#undef SVIT_LNF
+    SVIT_LAUNCH_CHECK("layernorm_fixed_kernel");
+    return SVIT_OK;
+  }
   const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
 #define SVIT_LN(T)                                                                                                  \
   layernorm_kernel<T><<<grid, wpb * 32, 0, stream>>>(x, x_gs, x_ld, gamma, beta, param_gs, (T*)y, y_gs, y_ld, rows, \
