@@ -227,7 +227,7 @@ __device__ __forceinline__ void chunk_exp(uint32_t tbuf, int c0, int Tn, float s
   for (int i = 0; i < W; i += 2) {
     const float2 x = ffma2(make_float2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc, of);
     float2 e;
-    if ((i >> 1) & 1)
+    if ((i >> 1) % 3 == 2)  // one pair in three (measured: 1/2 270 us, 1/3 260 us, 1/4 262 us per 1 024 x 12 heads)
       e = ex2_poly2(x);  // FMA / ALU pipes
     else
       e = make_float2(ex2_approx(x.x), ex2_approx(x.y));  // MUFU pipe
