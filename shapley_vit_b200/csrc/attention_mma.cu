@@ -188,7 +188,9 @@ int dispatch_kt(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, cu
 // tiles (x = hi + lo to ~2^-22); every product runs hi*hi + hi*lo + lo*hi into the fp32
 // accumulators -- scores and P V both -- with P split in registers after the fp32 softmax.
 // ~21 significant bits end to end at three MMAs per tile: the attention of the f16x3 mode.
-constexpr int kWarps3 = 8;
+// Only K and V are staged (hi + lo: 4 x 26 KB for T = 197), Q fragments are read from global memory and
+// split in registers, so two CTAs of four warps fit an SM and cover each other's staging phase and tail.
+constexpr int kWarps3 = 4;
 
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
   hi = pack_f16x2_sat(x, y);
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const flo
   constexpr int TP = KT * 16;
   constexpr int TILE = TP * 128;
   extern __shared__ __align__(128) unsigned char att_raw[];
-  unsigned char* Qh = att_raw;  // Qh | Ql | Kh | Kl | Vh | Vl
+  unsigned char* Kh = att_raw;  // Kh | Kl | Vh | Vl
   const int h = heads * kD;
   const int64_t seq = blockIdx.x;
   const int head = blockIdx.y;
@@ -226,20 +228,19 @@ __global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const flo
     const uint32_t off = tile_off(row, chunk);
     if (row < Tn) {
       const float* src = base + (size_t)row * 3 * h + chunk * 8;
-      split8(src, Qh, Qh + TILE, off);
-      split8(src + h, Qh + 2 * TILE, Qh + 3 * TILE, off);
-      split8(src + 2 * h, Qh + 4 * TILE, Qh + 5 * TILE, off);
+      split8(src + h, Kh, Kh + TILE, off);
+      split8(src + 2 * h, Kh + 2 * TILE, Kh + 3 * TILE, off);
     } else {
       const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int m = 0; m < 6; ++m) *reinterpret_cast<uint4*>(Qh + m * TILE + off) = z;
+      for (int m = 0; m < 4; ++m) *reinterpret_cast<uint4*>(Kh + m * TILE + off) = z;
     }
   }
   __syncthreads();
 
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const uint32_t q_base = smem_u32a(Qh), k_base = q_base + 2 * TILE, v_base = q_base + 4 * TILE;
+  const uint32_t k_base = smem_u32a(Kh), v_base = k_base + 2 * TILE;
   const float sl2 = 0.125f * 1.4426950408889634f;  // d^-0.5 * log2(e), d = 64
   const int lm = lane >> 3, lr = lane & 7;
   using M = Mma<__half>;
@@ -251,10 +252,22 @@ __global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const flo
     for (int nt = 0; nt < 2 * KT; ++nt) S[nt][0] = S[nt][1] = S[nt][2] = S[nt][3] = 0.f;
 #pragma unroll
     for (int ks = 0; ks < kD / 16; ++ks) {
+      // A fragments of m16n8k16 straight from global memory: rows g / g + 8, columns 2t, 2t+1 (+8) of the k-block
       uint32_t ah[4], al[4];
-      const uint32_t qo = tile_off(r0 + lr + (lm & 1) * 8, ks * 2 + (lm >> 1));
-      ldsm_x4(ah[0], ah[1], ah[2], ah[3], q_base + qo);
-      ldsm_x4(al[0], al[1], al[2], al[3], q_base + TILE + qo);
+      {
+        const float* qa = base + (size_t)(r0 + g) * 3 * h + ks * 16 + 2 * t;
+        const float* qb = qa + (size_t)8 * 3 * h;
+        const float2 z = make_float2(0.f, 0.f);
+        const bool va = r0 + g < Tn, vb = r0 + g + 8 < Tn;
+        const float2 q0 = va ? __ldg(reinterpret_cast<const float2*>(qa)) : z;
+        const float2 q1 = vb ? __ldg(reinterpret_cast<const float2*>(qb)) : z;
+        const float2 q2 = va ? __ldg(reinterpret_cast<const float2*>(qa + 8)) : z;
+        const float2 q3 = vb ? __ldg(reinterpret_cast<const float2*>(qb + 8)) : z;
+        split2(q0.x, q0.y, ah[0], al[0]);
+        split2(q1.x, q1.y, ah[1], al[1]);
+        split2(q2.x, q2.y, ah[2], al[2]);
+        split2(q3.x, q3.y, ah[3], al[3]);
+      }
 #pragma unroll
       for (int np = 0; np < KT; ++np) {
         uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const flo
 
 template <int KT>
 int launch_split(const float* qkv, float* ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
-  const size_t smem = (size_t)6 * KT * 16 * 128;
+  const size_t smem = (size_t)4 * KT * 16 * 128;
   auto kern = attention_split_kernel<KT>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)n_seq, heads);
