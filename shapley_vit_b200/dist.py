@@ -48,18 +48,34 @@ def shard_bounds(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
     return lo, min(lo + per, n_items)
 
 
-def sharded_evaluate(evaluate: Callable[[Sequence[Sequence[float]]], Tuple[List[int], List[float]]],
-                     rows: Sequence[Sequence[float]]) -> Tuple[List[int], List[float]]:
-    """Evaluate ``rows`` (dense ratio rows) split across ranks; every rank returns all results."""
+def sharded_evaluate(evaluate: Callable[..., Tuple[List[int], List[float]]],
+                     rows: Sequence[Sequence[float]], n_val: int = 0) -> Tuple[List[int], List[float]]:
+    """Evaluate ``rows`` (dense ratio rows) across ranks; every rank returns all results.
+
+    Two axes:
+    * at least one row per rank: contiguous slices of the rows, one all-gather of the (correct, loss_sum)
+      pairs -- each pair is produced by one rank, so the result does not depend on the world size;
+    * fewer rows than ranks (late truncation waves, tiny games) and ``n_val`` given: every rank evaluates
+      ALL rows on its slice of the validation images (``evaluate(rows, image_range=(lo, hi))``) and one
+      all-reduce sums the pairs -- integer counts stay exact, the fp64 loss sums differ from the
+      single-rank value only by the order of the final additions."""
     rank, ws = world()
     if ws == 1:
         return evaluate(rows)
     td = _td()
     n = len(rows)
+    dev = _comm_device()
+    if 0 < n < ws and n_val >= ws:
+        lo, hi = shard_bounds(n_val, rank, ws)
+        c, l = evaluate(rows, image_range=(lo, hi))
+        tc = torch.tensor(c, dtype=torch.int64, device=dev)
+        tl = torch.tensor(l, dtype=torch.float64, device=dev)
+        td.all_reduce(tc)
+        td.all_reduce(tl)
+        return tc.cpu().tolist(), tl.cpu().tolist()
     per = (n + ws - 1) // ws
     lo, hi = shard_bounds(n, rank, ws)
     c, l = evaluate(rows[lo:hi]) if hi > lo else ([], [])
-    dev = _comm_device()
     mine_c = torch.zeros(per, dtype=torch.int64, device=dev)
     mine_l = torch.zeros(per, dtype=torch.float64, device=dev)
     if hi > lo:

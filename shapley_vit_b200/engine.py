@@ -152,8 +152,10 @@ class CoalitionEngine:
         ops.aggregate(self.deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
         ops.aggregate(self.deltas[:, V:], w0m, ratios, out=self.wmat[:Cn], P=Mz)
 
-    def _run_batch(self, ratio_rows: Sequence[Sequence[float]]) -> Tuple[torch.Tensor, torch.Tensor]:
-        """One batch of <= coalition_batch coalitions given their dense ratio rows."""
+    def _run_batch(self, ratio_rows: Sequence[Sequence[float]],
+                   image_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """One batch of <= coalition_batch coalitions given their dense ratio rows, scored on the validation
+        images [lo, hi) (default: all of them)."""
         Cn = len(ratio_rows)
         lay, cfg = self.lay, self.cfg
         # FedAvg ratios: fp64 on the host (as the reference computes them), rounded once to fp32;
@@ -168,12 +170,19 @@ class CoalitionEngine:
             self.agg_spans.append((e0, e1))
         logits = self.logits[:Cn]
         npch = cfg.n_patches
-        for s in range(0, self.n_val, self.image_chunk):
-            b = min(self.image_chunk, self.n_val - s)
+        lo, hi = image_range if image_range is not None else (0, self.n_val)
+        for s in range(lo, hi, self.image_chunk):
+            b = min(self.image_chunk, hi - s)
             self.plan.forward(self.wvec[:Cn], self.wmat[:Cn], self.patches[s * npch:(s + b) * npch], b, logits,
                               image_offset=s)
-        self.kernel_launches += 2 + ((self.n_val + self.image_chunk - 1) // self.image_chunk) * (3 + 7 * cfg.layers) + 1
-        correct, loss = ops.score(logits, self.labels)
+        self.kernel_launches += 2 + ((hi - lo + self.image_chunk - 1) // self.image_chunk) * (3 + 7 * cfg.layers) + 1
+        if (lo, hi) == (0, self.n_val):
+            correct, loss = ops.score(logits, self.labels)
+        elif hi > lo:
+            correct, loss = ops.score(logits[:, lo:hi], self.labels[lo:hi])
+        else:
+            correct = torch.zeros(Cn, dtype=torch.int64, device=self.device)
+            loss = torch.zeros(Cn, dtype=torch.float64, device=self.device)
         if self.keep_logits:
             self.last_logits = logits.clone()
         return correct, loss
@@ -264,15 +273,17 @@ class CoalitionEngine:
             row[int(j)] = float(r)
         return row
 
-    def evaluate(self, ratio_rows: Sequence[Sequence[float]]) -> Tuple[List[int], List[float]]:
+    def evaluate(self, ratio_rows: Sequence[Sequence[float]],
+                 image_range: Optional[Tuple[int, int]] = None) -> Tuple[List[int], List[float]]:
         """Evaluate coalitions given as dense FedAvg ratio rows [n_clients] (0 = non-member).
-        Returns per coalition (#correct, sum of cross-entropy) over the validation set."""
+        Returns per coalition (#correct, sum of cross-entropy) over the validation set, or over its
+        images [lo, hi) when ``image_range`` is given (the validation-split axis of dist.sharded_evaluate)."""
         correct: List[int] = []
         loss: List[float] = []
         with torch.cuda.device(self.device):
             pending = []
             for s in range(0, len(ratio_rows), self.coalition_batch):
-                c, l = self._run_batch(ratio_rows[s:s + self.coalition_batch])
+                c, l = self._run_batch(ratio_rows[s:s + self.coalition_batch], image_range)
                 pending.append((c, l))
             for c, l in pending:       # single host sync at the end
                 correct += c.cpu().tolist()

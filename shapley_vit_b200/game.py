@@ -113,9 +113,11 @@ class Game:
                     row = [0.0] * self._n_all
                 rows.append(row)
                 row_keys.append(k)
-            evaluator = self._evaluator.evaluate if self._evaluator is not None else self.engine.evaluate
-            correct, loss_sum = dist.sharded_evaluate(evaluator, rows)
+            ev = self._evaluator if self._evaluator is not None else self.engine
             n_val = self._n_val()
+            # fewer pending coalitions than ranks: split the validation set instead (if the evaluator can)
+            can_split = self._evaluator is None or getattr(self._evaluator, "supports_image_range", False)
+            correct, loss_sum = dist.sharded_evaluate(ev.evaluate, rows, n_val if can_split else 0)
             for k, c, l in zip(row_keys, correct, loss_sum):
                 if math.isnan(l):
                     raise ValueError("loss is nan")

@@ -30,7 +30,12 @@ def main():
     game._evaluator = OracleEvaluator(cfg, w0, deltas, images, labels)
     sv = estimators.shapley_exact(game)
     rank, ws = dist.world()
-    res = dict(rank=rank, world=ws, evaluated_here=sum(game._evaluator.calls),
+    # one pending coalition, two ranks: the validation-split axis (every rank scores its half, one all-reduce)
+    game2 = Game(clients, ServerBase({}, w0, clients, None, None, None), w0, deltas, [True] * 3, prev, 2, {})
+    game2._evaluator = OracleEvaluator(cfg, w0, deltas, images, labels)
+    u_single = game2.eval_utility((0, 2))
+    split = dict(utility=u_single, counts=list(game2.counts[frozenset((0, 2))]), ranges=game2._evaluator.ranges)
+    res = dict(rank=rank, world=ws, evaluated_here=sum(game._evaluator.calls), split=split,
                counts={",".join(map(str, sorted(k))): v for k, v in game.counts.items()},
                sv=[[sv[d][c] for c in range(3)] for d in range(2)],
                bounds=[dist.shard_bounds(7, r, ws) for r in range(ws)])

@@ -49,6 +49,14 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
         assert r["counts"] == single["counts"]          # integer counts and fp64 loss sums, bit-identical
         assert r["sv"] == single["sv"]
     assert ranks[0]["bounds"] == [[0, 4], [4, 7]]
+    # one coalition for two ranks: each rank scored its half of the 32 validation images, the all-reduced
+    # count is exact and the fp64 loss sum equals the single-process one up to the order of the last addition
+    assert [r["split"]["ranges"] for r in ranks] == [[[0, 16]], [[16, 32]]] and single["split"]["ranges"] == [None]
+    for r in ranks:
+        assert r["split"]["counts"][0] == single["split"]["counts"][0]
+        assert r["split"]["counts"][1] == pytest.approx(single["split"]["counts"][1], rel=1e-12)
+        assert r["split"]["utility"][0] == single["split"]["utility"][0]
+    assert ranks[0]["split"] == ranks[1]["split"] or ranks[0]["split"]["counts"] == ranks[1]["split"]["counts"]
 
 
 def test_shard_bounds_cover_everything():

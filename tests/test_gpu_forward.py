@@ -175,3 +175,17 @@ def test_module_forward_and_evaluation_api():
     acc, loss = evaluation({"precision": "f32"}, net, loader)
     racc, rloss = restate.evaluation(w0, cfg, images, labels)
     assert acc == racc and loss == pytest.approx(rloss, rel=1e-5)
+
+
+def test_validation_split_axis_sums_to_the_whole():
+    """engine.evaluate(rows, image_range=...) -- the axis dist.sharded_evaluate takes when there are fewer pending
+    coalitions than ranks: the per-slice (correct, loss_sum) pairs add up to the whole-set pair (counts exactly)."""
+    cfg, w0, _, deltas, n_train, images, labels = synthetic_game(n_clients=3, n_val=200, layers=2, seed=6)
+    eng = make_engine(cfg, w0, deltas, images, labels, "f32", coalition_batch=2, image_chunk=64)
+    rows = ratio_rows([(0, 1), (2,), (0, 1, 2)], n_train)
+    whole_c, whole_l = eng.evaluate(rows)
+    parts = [eng.evaluate(rows, image_range=r) for r in ((0, 67), (67, 134), (134, 200), (200, 200))]
+    for ci in range(3):
+        assert sum(p[0][ci] for p in parts) == whole_c[ci]
+        assert sum(p[1][ci] for p in parts) == pytest.approx(whole_l[ci], rel=1e-12)
+    assert parts[3] == ([0, 0, 0], [0.0, 0.0, 0.0])
