@@ -102,8 +102,14 @@ def evaluation(args, net, eval_loader):
     args = args if isinstance(args, dict) else {}
     precision = _lib.PRECISIONS[args.get("precision", "f16")]
     device = args.get("device", "cuda:0")
-    cfg = config_of(net, args.get("heads"))
     sd = _clean_keys(_state_dict_of(net))
+    if any(".lora_A." in k for k in sd):   # PEFT-LoRA model (reference start.py:274-283): fold the factors in
+        from . import lora
+        from .models.vit import infer_config
+        sd = lora.merged_state_dict(sd, args.get("lora_alpha", 8.0))
+        cfg = getattr(net, "cfg", None) or infer_config(sd, heads=args.get("heads"))
+    else:
+        cfg = config_of(net, args.get("heads"))
     val = _EvalCache.get(eval_loader, cfg, precision, device)
     eng = CoalitionEngine(cfg, None, [sd], val, precision=precision, coalition_batch=1,
                           image_chunk=args.get("image_chunk", 128), device=device)

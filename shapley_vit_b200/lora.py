@@ -97,6 +97,23 @@ def pack_lora(cfg: VitConfig, lora: LoraDict, r: int, scaling: float, out: Optio
     return out
 
 
+def merged_state_dict(sd, lora_alpha: float = 8.0) -> "OrderedDict[str, torch.Tensor]":
+    """Plain HF-keyed state_dict of ONE PEFT-LoRA model with W + (alpha / r) B A folded into the wrapped
+    projections (host fp32): what scoring a single explicit model needs (``fl.evaluation``)."""
+    hf, lo = split_state_dict(sd)
+    if not lo:
+        return hf
+    scaling = float(lora_alpha) / lora_rank(lo)
+    out = OrderedDict((k, v) for k, v in hf.items())
+    for (layer, target, ab), a in lo.items():
+        if ab != "A":
+            continue
+        b = lo[(layer, target, "B")]
+        key = f"vit.encoder.layer.{layer}.attention.attention.{target}.weight"
+        out[key] = hf[key].to(torch.float32) + scaling * (b.to(torch.float32) @ a.to(torch.float32))
+    return out
+
+
 class LoraCoalitionEngine(CoalitionEngine):
     """CoalitionEngine for PEFT-LoRA client models: same evaluate()/Game interface, state_dicts with LoRA keys."""
 

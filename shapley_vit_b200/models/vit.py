@@ -53,6 +53,18 @@ class ViTForImageClassification(nn.Module):
             else:
                 p.copy_(torch.randn(p.shape, generator=g) * std)
 
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts checkpoints saved from ``nn.DataParallel`` / PEFT wrappers: leading ``module.`` (and, for the
+        plain ViT, ``base_model.model.``) prefixes are dropped when the bare key is one of this module's."""
+        own = set(self.state_dict().keys())
+        fixed = {}
+        for k, v in state_dict.items():
+            kk = k
+            while kk not in own and (kk.startswith("module.") or kk.startswith("base_model.model.")):
+                kk = kk[len("module."):] if kk.startswith("module.") else kk[len("base_model.model."):]
+            fixed[kk] = v
+        return super().load_state_dict(fixed, strict=strict, **kw)
+
     @property
     def config(self):  # a few HF-style attribute names
         c = self.cfg
@@ -82,6 +94,64 @@ class ViTForImageClassification(nn.Module):
         logits = torch.empty((1, B, self.cfg.n_cls), dtype=torch.float32, device=dev)
         plan.forward(wvec, wmat, patches, B, logits)
         return SimpleNamespace(logits=logits[0])
+
+
+def peft_state_dict_spec(cfg: VitConfig, r: int):
+    """(key, shape) of a PEFT-LoRA wrapped HF ViT as the reference builds it (start.py:274-283): ``query`` and
+    ``value`` wrapped (``base_layer`` + ``lora_A/B.default``), classifier in ``modules_to_save``."""
+    out = []
+    h = cfg.hidden
+    for key, shape in state_dict_spec(cfg):
+        stem, leaf = key.rsplit(".", 1)
+        if stem.endswith("attention.attention.query") or stem.endswith("attention.attention.value"):
+            out.append((f"base_model.model.{stem}.base_layer.{leaf}", shape))
+            if leaf == "weight":
+                out.append((f"base_model.model.{stem}.lora_A.default.weight", (r, h)))
+                out.append((f"base_model.model.{stem}.lora_B.default.weight", (h, r)))
+        elif key.startswith("classifier."):
+            out.append((f"base_model.model.classifier.original_module.{leaf}", shape))
+            out.append((f"base_model.model.classifier.modules_to_save.default.{leaf}", shape))
+        else:
+            out.append((f"base_model.model.{key}", shape))
+    return out
+
+
+class LoraViTForImageClassification(ViTForImageClassification):
+    """Parameter container with the state_dict keys of ``get_peft_model(vit, LoraConfig(r, lora_alpha,
+    target_modules=['query', 'value'], modules_to_save=['classifier']))`` (reference start.py:274-276), so the
+    author's client checkpoints load unchanged.  PEFT's init: A Kaiming-uniform, B zero.  ``forward`` scores the
+    merged model W + (alpha / r) B A."""
+
+    def __init__(self, cfg: VitConfig, r: int = 16, lora_alpha: float = 8.0, precision: str = "f16"):
+        nn.Module.__init__(self)
+        self.cfg, self.precision, self.r, self.lora_alpha = cfg, precision, r, lora_alpha
+        self._names = []
+        for key, shape in peft_state_dict_spec(cfg, r):
+            self._register(key, nn.Parameter(torch.empty(shape, dtype=torch.float32), requires_grad=False))
+        self.reset_parameters()
+        self._plan = None
+
+    @torch.no_grad()
+    def reset_parameters(self, std: float = 0.02, seed: Optional[int] = None) -> None:
+        g = torch.Generator().manual_seed(seed) if seed is not None else None
+        for name, p in self.named_parameters():
+            if ".lora_B." in name or name.endswith("bias"):
+                p.zero_()
+            elif ".lora_A." in name:
+                bound = (1.0 / p.shape[1]) ** 0.5          # kaiming_uniform_(a = sqrt(5)) on [r, h]
+                p.copy_((torch.rand(p.shape, generator=g) * 2 - 1) * bound)
+            elif "layernorm" in name and name.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * std)
+
+    @torch.no_grad()
+    def forward(self, pixel_values: torch.Tensor):
+        from ..lora import merged_state_dict
+
+        plain = ViTForImageClassification(self.cfg, precision=self.precision)
+        plain.load_state_dict(merged_state_dict(self.state_dict(), self.lora_alpha))
+        return plain(pixel_values)
 
 
 def infer_config(sd: Dict[str, torch.Tensor], heads: Optional[int] = None, ln_eps: float = 1e-12) -> VitConfig:

@@ -75,6 +75,10 @@ _NEW_FLAGS = [
     (("--image-size", "--image_size"), dict(type=int, default=224, help="ViT input resolution")),
     (("--num-classes", "--num_classes"), dict(type=int, default=4, help="classifier width (reference: 4)")),
     (("--dtype",), dict(type=str, default="f16", help="GEMM operand precision: f16 | bf16 | tf32 | f16x3 | f32")),
+    (("--lora-rank", "--lora_rank"), dict(type=int, default=0,
+                                          help="> 0: PEFT-LoRA wrapped ViT (query / value, classifier saved) as in the "
+                                               "reference's start.py:274-276 (there: 16); 0: plain ViT")),
+    (("--lora-alpha", "--lora_alpha"), dict(type=float, default=8.0, help="LoRA alpha (reference: 8)")),
     (("--synthetic",), dict(action=_STORE_TRUE, default=False, help="synthetic validation set and client models")),
     (("--val-size", "--val_size"), dict(type=int, default=1000, help="synthetic validation images")),
 ]

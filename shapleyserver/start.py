@@ -47,7 +47,7 @@ LAST_SHAPLEY_VALUE = None
 
 def _loop_args():
     return {"precision": opt.dtype, "coalition_batch": opt.coalition_batch, "image_chunk": opt.image_chunk,
-            "approximation_method": opt.approximation_method, "seed": opt.seed,
+            "approximation_method": opt.approximation_method, "seed": opt.seed, "lora_alpha": opt.lora_alpha,
             **({"m": opt.mc_samples} if opt.mc_samples else {})}
 
 
@@ -152,16 +152,26 @@ def start():
     dataset = getOCTData2()
     num_clients = opt.num_clients or opt.dist_num
     cfg = layout.vit_preset(opt.vit_size, image=opt.image_size, n_cls=opt.num_classes)
-    init_global_model = ViTForImageClassification(cfg, precision=opt.dtype)
+    def new_model():
+        if opt.lora_rank > 0:   # the reference's get_peft_model(vit, LoraConfig(r=16, lora_alpha=8, ...)), start.py:274-276
+            from shapley_vit_b200.models.vit import LoraViTForImageClassification
+            return LoraViTForImageClassification(cfg, r=opt.lora_rank, lora_alpha=opt.lora_alpha, precision=opt.dtype)
+        return ViTForImageClassification(cfg, precision=opt.dtype)
+
+    init_global_model = new_model()
     client_sizes = None
     if opt.synthetic:
         seed = opt.seed or 0
-        w0 = synth.make_state_dict(cfg, seed)
+        if opt.lora_rank > 0:
+            w0, client_sds = synth.make_peft_state_dicts(cfg, num_clients, seed, r=opt.lora_rank, prefix="base_model.model.")
+        else:
+            w0 = synth.make_state_dict(cfg, seed)
+            client_sds = [synth.make_client_state_dict(w0, j, seed) for j in range(num_clients)]
         init_global_model.load_state_dict(w0)
         client_models = []
-        for j in range(num_clients):
-            m = ViTForImageClassification(cfg, precision=opt.dtype)
-            m.load_state_dict(synth.make_client_state_dict(w0, j, seed))
+        for sd in client_sds:
+            m = new_model()
+            m.load_state_dict(sd)
             client_models.append(m)
         client_sizes = synth.client_sizes(num_clients)
     else:
