@@ -141,8 +141,9 @@ class LoraCoalitionEngine(CoalitionEngine):
             self.qv_off = [self.lay.find(kind, l).offset for l in range(L) for kind in (K_WQ, K_WV)]
             # the author's case: nothing but LoRA (and the vec region: classifier, biases) differs between clients
             self.base_frozen = not bool(self.deltas[:, V:].any().item())
+            self._eye = torch.eye(cb, dtype=torch.float32)               # K1 as a row-wise cast: out[c] = 1 * rows[c]
             if self.base_frozen:
-                self.wmat[:] = self.w0[V:].to(self.wmat.dtype)
+                ops.aggregate(self.w0[V:].unsqueeze(0), None, torch.ones((cb, 1)), out=self.wmat, P=self.lay.mat_size)
                 self.qv_base = torch.stack([self.w0[V + o:V + o + h * h] for o in self.qv_off])   # [n_proj, h*h] fp32
             torch.cuda.synchronize(self.device)
 
@@ -163,9 +164,10 @@ class LoraCoalitionEngine(CoalitionEngine):
         f = self.lora_s[:Cn].view(Cn * self.n_proj, 2, h, r)
         w = qv.view(Cn * self.n_proj, h, h)
         ops.gemm(_lib.PREC_F32, f[:, 1], f[:, 0], residual=w, out=w, out_dtype=torch.float32)
-        for i, o in enumerate(self.qv_off):
-            self.wmat[:Cn, o:o + hh].copy_(qv[:, i])
-        self.kernel_launches += 2 + (0 if self.base_frozen else 1 + self.n_proj)
+        eye = self._eye[:Cn, :Cn]
+        for i, o in enumerate(self.qv_off):                            # fp32 blocks -> operand dtype, in place in wmat
+            ops.aggregate(qv[:, i], None, eye, out=self.wmat[:Cn, o:o + hh], P=hh)
+        self.kernel_launches += 2 + self.n_proj + (0 if self.base_frozen else 1 + self.n_proj)
 
     def merged_rows(self, ratio_rows) -> torch.Tensor:
         """fp32 [C, n_proj, h, h]: the merged query / value weights of each coalition (tests)."""
