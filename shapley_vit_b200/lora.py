@@ -169,6 +169,14 @@ class LoraCoalitionEngine(CoalitionEngine):
             ops.aggregate(qv[:, i], None, eye, out=self.wmat[:Cn, o:o + hh], P=hh)
         self.kernel_launches += 2 + self.n_proj + (0 if self.base_frozen else 1 + self.n_proj)
 
+    def evaluate_state_dict(self, sd) -> Tuple[int, float]:
+        """Score one explicit model; PEFT-keyed state_dicts are merged on the host first."""
+        out = super().evaluate_state_dict(merged_state_dict(sd, self.scaling * self.r) if is_lora_state_dict(sd) else sd)
+        if self.base_frozen:   # the call went through wmat[0]: restore the W_0 rows the frozen-base path relies on
+            V = self.lay.vec_size
+            ops.aggregate(self.w0[V:].unsqueeze(0), None, torch.ones((1, 1)), out=self.wmat[:1], P=self.lay.mat_size)
+        return out
+
     def merged_rows(self, ratio_rows) -> torch.Tensor:
         """fp32 [C, n_proj, h, h]: the merged query / value weights of each coalition (tests)."""
         ratios = torch.as_tensor(ratio_rows, dtype=torch.float64).to(torch.float32)

@@ -108,6 +108,22 @@ def test_lora_coalition_logits_and_counts(prec, tol, frozen):
 
 
 @pytest.mark.gpu
+def test_lora_engine_scores_one_explicit_model_and_keeps_its_frozen_base():
+    cfg, w0, deltas, n_train, images, labels = peft_game()
+    eng = lora.LoraCoalitionEngine(cfg, w0, deltas, images, labels, lora_alpha=ALPHA, precision="f32", coalition_batch=2,
+                                   image_chunk=32)
+    rows = ratio_rows([(0, 1), (2,)], n_train)
+    before = eng.evaluate(rows)
+    client0 = {k: w0[k] + deltas[0][k] for k in w0}
+    c, l = eng.evaluate_state_dict(client0)
+    hf, lo = restate.split_peft_state_dict(client0)
+    want = restate.vit_forward(hf, cfg, images, lora=lo, lora_scaling=ALPHA / R)
+    assert c == int((want.argmax(1) == labels).sum())
+    assert l == pytest.approx(torch.nn.functional.cross_entropy(want.double(), labels, reduction="sum").item(), rel=1e-5)
+    assert eng.evaluate(rows) == before          # the matrix region still holds W_0 where the frozen path expects it
+
+
+@pytest.mark.gpu
 def test_game_detects_peft_state_dicts():
     """The drop-in Game takes the PEFT-keyed init model and client deltas as they are (start.py:285-288)."""
     from shapley_vit_b200 import estimators
