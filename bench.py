@@ -268,7 +268,7 @@ def parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev):
 def run_ours(a):
     import torch
 
-    from shapley_vit_b200 import _lib, dist, layout, ops, synth
+    from shapley_vit_b200 import _lib, dist, layout, synth
     from shapley_vit_b200.engine import CoalitionEngine, ValidationSet
     from shapley_vit_b200.fl import ClientBase, ServerBase
     from shapley_vit_b200.game import Game

@@ -16,7 +16,6 @@ once and stay in HBM.
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch

@@ -20,7 +20,7 @@ from __future__ import annotations
 import math
 import random
 from itertools import chain, combinations
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, Iterable, List, Optional, Tuple
 
 import numpy as np
 

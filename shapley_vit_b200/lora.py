@@ -30,7 +30,7 @@ from __future__ import annotations
 
 import re
 from collections import OrderedDict
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import torch
 

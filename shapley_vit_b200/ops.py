@@ -5,12 +5,12 @@ on these paths, and there is no fallback if the library is missing."""
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
 
 from . import _lib
-from ._lib import BF16, F16, F32, PREC_BF16, PREC_F16, PREC_F16X3, PREC_F32, PREC_TF32, EpilogueC, check
+from ._lib import BF16, F16, F32, PREC_F16X3, EpilogueC, check
 
 TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16, F16: torch.float16}
 SVIT_DTYPE = {v: k for k, v in TORCH_DTYPE.items()}

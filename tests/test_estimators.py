@@ -1,6 +1,5 @@
 """The product's estimators (host logic) against outputs of the reference's own estimators
 (tests/golden/estimators.json and the estimator block of cfg1_tiny.json), same seeds."""
-import random
 
 import numpy as np
 import pytest

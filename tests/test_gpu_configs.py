@@ -5,7 +5,6 @@ import random
 
 import numpy as np
 import pytest
-import torch
 
 from helpers import synthetic_game
 from oracle import restate

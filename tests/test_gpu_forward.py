@@ -10,7 +10,6 @@ loss tolerances and to the agreement each precision can deliver (>= 99.5 % fp16/
 the measured agreement is printed and recorded in DESIGN.md."""
 # per-precision gates: (min top-1 agreement, max |d correct| in samples, max |d mean loss|)
 GATES = {"f32": (0.999, 0, 1e-5), "f16x3": (0.999, 1, 2e-5), "tf32": (0.995, 4, 2e-3), "f16": (0.995, 4, 2e-3), "bf16": (0.98, 12, 1e-2)}
-import numpy as np
 import pytest
 import torch
 
