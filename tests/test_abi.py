@@ -63,3 +63,29 @@ def test_product_has_no_cpu_path():
         pytest.skip("CPU-only check")
     with pytest.raises(ValueError, match="CUDA"):
         ops.aggregate(torch.zeros(1, 8), None, torch.ones(1, 1))
+
+
+def test_f16x3_plan_has_fp32_operands_and_split_scratch():
+    """The split-precision mode stores fp32 operands (weights, patches) and adds the [hi | lo] scratch to the workspace."""
+    from shapley_vit_b200.layout import VitConfig
+
+    lib = _lib.load()
+    cfg = _lib.cfg_struct(VitConfig(192, 2, 3, 768, 32, 10))
+    sizes = {}
+    for name in ("f16", "tf32", "f16x3"):
+        h = C.c_void_p()
+        assert lib.svit_plan_create(C.byref(cfg), _lib.PRECISIONS[name], 2, 4, C.byref(h)) == 0
+        sizes[name] = (lib.svit_plan_operand_dtype(h), lib.svit_plan_workspace_bytes(h))
+        assert lib.svit_plan_destroy(h) == 0
+    assert sizes["f16x3"][0] == _lib.F32 == sizes["tf32"][0] and sizes["f16"][0] == _lib.F16
+    assert sizes["f16x3"][1] > sizes["tf32"][1] > sizes["f16"][1]
+    h = C.c_void_p()
+    assert lib.svit_plan_create(C.byref(cfg), 7, 2, 4, C.byref(h)) == -1          # unknown precision
+
+
+def test_lib_override_must_exist(monkeypatch):
+    """SVIT_LIB (A/B against another build of the same ABI) fails loudly on a bad path; there is no fallback."""
+    monkeypatch.setenv("SVIT_LIB", "/nonexistent/libsvit.so")
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(RuntimeError):
+        _lib.load()
