@@ -104,7 +104,8 @@ int svit_layout_segment(const svit_vit_cfg* cfg, int32_t index, svit_segment* ou
  * For out_dtype SVIT_F32 every product and every sum is rounded to fp32 separately (no FMA
  * contraction), i.e. exactly the arithmetic of get_aggregated_model followed by model_agg_lazy.
  * For the 16-bit out_dtypes (the operand feed of the 16-bit GEMMs; the reference has no such
- * format) the accumulation is fused (<= 1 fp32 ulp from the above before the cast to 16 bits).
+ * format) the accumulation is fused and starts from w0 (a few fp32 ulp from the above before the
+ * cast to 16 bits; svit_aggregate_onto keeps base + sum for every out_dtype).
  * The [N, P] stack is read from HBM ONCE for all C coalitions.
  *   deltas  device [N, delta_stride] fp32     w0   device [P] fp32 (NULL = zeros)
  *   ratios  HOST   [C, N] fp32, 0 for non-members (FedAvg n_j / sum n over the coalition); they are
