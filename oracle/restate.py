@@ -13,6 +13,12 @@ the build container through ``oracle/ref_shim.py`` with HF's
 generating script and ``tests/golden/*.npz|json`` the committed fixtures
 (``tests/test_oracle_golden.py`` checks this file against them).
 
+One exception, said where it applies: the LoRA branch (``split_peft_state_dict`` and
+``vit_forward(..., lora=...)``) restates PEFT's published
+``lora.Linear`` forward -- ``peft`` is not installed in the build container, so for
+that row the parity is UNPINNED (the entry-wise aggregation underneath it is the
+reference's own, pinned as above).
+
 Each function cites the reference lines it follows.  All arithmetic is fp32 on
 CPU tensors, in the reference's operation order.
 """
