@@ -17,6 +17,8 @@ so parity is pinned on outputs of the reference's own code driven here through
   8 images: logits for three coalitions (pins the restated forward at the
   BASELINE config 2 geometry);
 * ``estimators``  -- every reference estimator on table-driven toy games;
+* ``fed_bookkeeping`` -- the numpy bookkeeping on utility tables of utils_fed_shapley.py
+  (:29-91, :253-259);
 * ``round_select`` -- the three MILP round selectors (fed_client_contribution/milp.py) on seeded
   selection matrices;
 * ``lazy_rounds`` -- the multi-round reconstruction ``compute_utilities_lazy``
@@ -342,11 +344,38 @@ def golden_round_select(ref):
     print("round_select done")
 
 
+def golden_fed_bookkeeping(ref):
+    """The numpy bookkeeping of utils_fed_shapley.py (:29-91, :253-259) on seeded utility tables."""
+    import importlib
+    import types
+
+    ufs = importlib.import_module("refshapleyserver.fed_client_contribution.utils_fed_shapley")
+    rng = np.random.RandomState(3)
+    out = []
+    for n, T, part in ((4, 3, [0, 2, 3]), (5, 4, [1, 2]), (3, 2, [0, 1, 2])):
+        all_subsets = ref.utils_shapley.powerset(range(n))
+        table = {k: float(rng.rand()) for k in all_subsets}
+        matrix = rng.rand(T, len(all_subsets))
+        args = types.SimpleNamespace(num_clients=n, num_users=n, epochs=T)
+        out.append({"n": n, "T": T, "participants": part, "table": [[list(k), v] for k, v in table.items()],
+                    "matrix": matrix.tolist(),
+                    "baseline": ufs.compute_shapley_value_baseline(args, table, part).tolist(),
+                    "groundtruth": ufs.compute_shapley_value_groundtruth(args, table).tolist(),
+                    "mask": ufs.roundly_mask(part, all_subsets).tolist(),
+                    "from_matrix": ufs.compute_shapley_value_from_matrix(args, matrix, all_subsets).tolist(),
+                    "selection": {str(k): v for k, v in ufs.get_selection_dict(n, part).items()}})
+    with open(os.path.join(GOLD, "fed_bookkeeping.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("fed_bookkeeping done")
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = ref_shim.load()
-    which = sys.argv[1:] or ["estimators", "cfg1", "base", "lazy", "rounds"]
+    which = sys.argv[1:] or ["estimators", "cfg1", "base", "lazy", "rounds", "fedbook"]
+    if "fedbook" in which:
+        golden_fed_bookkeeping(ref)
     if "rounds" in which:
         golden_round_select(ref)
     if "estimators" in which:

@@ -98,3 +98,63 @@ def compute_utilities_lazy(args, previous_utility, client_model_all_rounds, clie
             utilities[d][all_subsets[S]] = u[d]
             utilities_dict[d][S] = u[d]
     return utilities, utilities_dict
+
+
+# --------------------------------------------------------------------------------------------------- #
+# Bookkeeping on the utility tables (host-side consumers of the utilities above; numpy only).
+# Drop-ins for utils_fed_shapley.py:29-91 and :253-259.  ``all_subsets`` / the utility dictionaries are
+# keyed by sorted tuples and, like the reference's ``powerset`` (utils_shapley.py:141-145), hold the
+# NON-EMPTY subsets only: the marginal contribution over the empty coalition is not part of these sums
+# (the reference's convention, kept so the numbers are the reference's).
+# --------------------------------------------------------------------------------------------------- #
+from .estimators import ncr  # noqa: E402
+
+
+def _marginal_terms(players: Sequence[int]):
+    """For every player i of ``players``: [(S, S + {i}, 1 / C(n - 1, |S|)) for the non-empty S without i]."""
+    n = len(players)
+    for pos, i in enumerate(players):
+        others = list(players[:pos]) + list(players[pos + 1:])
+        yield i, [(S, tuple(sorted(S + (i,))), 1.0 / ncr(n - 1, len(S))) for S in powerset(others)]
+
+
+def compute_shapley_value_baseline(args, utilities_dict: Dict[Tuple[int, ...], float], idxs_users) -> np.ndarray:
+    """Per-round Shapley values of the round's PARTICIPANTS (utils_fed_shapley.py:29-42); zeros elsewhere."""
+    out = np.zeros(_num_clients(args, ()))
+    players = list(idxs_users)
+    for i, terms in _marginal_terms(players):
+        out[i] = sum((utilities_dict[si] - utilities_dict[s]) * w for s, si, w in terms) / len(players)
+    return out
+
+
+def compute_shapley_value_groundtruth(args, utilities_dict: Dict[Tuple[int, ...], float]) -> np.ndarray:
+    """The same over all ``args.num_users`` clients (utils_fed_shapley.py:45-58)."""
+    n = int(args.num_users)
+    out = np.zeros(n)
+    for i, terms in _marginal_terms(list(range(n))):
+        out[i] = sum((utilities_dict[si] - utilities_dict[s]) * w for s, si, w in terms) / n
+    return out
+
+
+def roundly_mask(idxs_users, all_subsets: Dict[Tuple[int, ...], int]) -> np.ndarray:
+    """1 at the column of every subset of the round's participants (utils_fed_shapley.py:61-68)."""
+    mask = np.zeros(len(all_subsets))
+    mask[[all_subsets[s] for s in powerset(idxs_users)]] = 1
+    return mask
+
+
+def compute_shapley_value_from_matrix(args, utility_matrix: np.ndarray, all_subsets: Dict[Tuple[int, ...], int]) -> np.ndarray:
+    """Shapley values summed over ``args.epochs`` rounds from the completed [rounds, subsets] utility matrix
+    (ComFedSV bookkeeping, utils_fed_shapley.py:71-91)."""
+    T, n = int(args.epochs), int(args.num_users)
+    per_subset = np.asarray(utility_matrix)[:T].sum(axis=0)          # the rounds enter only through their sum
+    out = np.zeros(n)
+    for i, terms in _marginal_terms(list(range(n))):
+        out[i] = sum((per_subset[all_subsets[si]] - per_subset[all_subsets[s]]) * w for s, si, w in terms) / n
+    return out
+
+
+def get_selection_dict(num_clients: int, idxs_participating_clients) -> Dict[int, bool]:
+    """{client: took part} (utils_fed_shapley.py:253-259)."""
+    chosen = set(int(i) for i in idxs_participating_clients)
+    return {i: i in chosen for i in range(num_clients)}
