@@ -364,6 +364,19 @@ def golden_fed_bookkeeping(ref):
                     "mask": ufs.roundly_mask(part, all_subsets).tolist(),
                     "from_matrix": ufs.compute_shapley_value_from_matrix(args, matrix, all_subsets).tolist(),
                     "selection": {str(k): v for k, v in ufs.get_selection_dict(n, part).items()}})
+    # ComFedSV (compared_methods.py:17-73): per-round values from the matrix, and one matrix row through a game
+    from oracle import toy_games
+    cm = ref.compared_methods
+    for rec, (n, T, part) in zip(out, ((4, 3, [0, 2, 3]), (5, 4, [1, 2]), (3, 2, [0, 1, 2]))):
+        all_subsets = ref.utils_shapley.powerset(range(n))
+        args = types.SimpleNamespace(num_clients=n, rounds=T)
+        with ref_shim.quiet():
+            per_round, _ = cm.comfedsv(args, np.array(rec["matrix"]), all_subsets)
+        rec["comfedsv"] = [[v[c] for c in range(n)] for v in per_round]
+        game = toy_games.ToyGame(n, seed=n, selection=[c in part for c in range(n)])
+        with ref_shim.quiet():
+            util, mask = cm.call_comfedsv(game, all_subsets, None)
+        rec["call_comfedsv"] = {"utilities": [u.tolist() for u in util], "mask": mask.tolist()}
     with open(os.path.join(GOLD, "fed_bookkeeping.json"), "w") as f:
         json.dump(out, f, indent=1)
     print("fed_bookkeeping done")

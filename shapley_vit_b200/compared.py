@@ -23,7 +23,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 from scipy.special import comb
 
-from .estimators import _prefetch, powerset
+from .estimators import _prefetch, ncr, powerset
 
 
 def shapley_value(utility: Dict[Tuple[int, ...], float], game) -> Dict[int, float]:
@@ -258,3 +258,49 @@ class Fed_SV(ShapleyValue):
                 return [float(v) for v in res.x[:n]]
             eps *= 1.1
         raise RuntimeError("group-testing feasibility problem has no solution")
+
+
+# --------------------------------------------------------------------------------------------------- #
+# ComFedSV bookkeeping (compared_methods.py:17-73)
+# --------------------------------------------------------------------------------------------------- #
+def roundly_mask(idxs_users, all_subsets):
+    """1 at the column of every non-empty subset of the round's participants (compared_methods.py:66-73)."""
+    mask = np.zeros(len(all_subsets))
+    mask[[all_subsets[s] for s in powerset(idxs_users)]] = 1
+    return mask
+
+
+def comfedsv(args, utility_matrix, all_subsets):
+    """Per-round Shapley values from the (completed) [rounds, subsets] utility matrix; unlike the per-table sums of
+    utils_fed_shapley.py this one counts the singleton's own utility as its margin over the empty coalition
+    (compared_methods.py:17-44).  Returns (list of {client: value} per round, seconds per round)."""
+    import time
+
+    T, N = int(args.rounds), int(args.num_clients)
+    terms = []
+    for cid in range(N):
+        others = [j for j in range(N) if j != cid]
+        terms.append([(all_subsets[S], all_subsets[tuple(sorted(S + (cid,)))], 1.0 / ncr(N - 1, len(S)))
+                      for S in powerset(others)])
+    per_round, seconds = [], []
+    for t in range(T):
+        t0 = time.time()
+        row = utility_matrix[t]
+        per_round.append({cid: (sum((row[b] - row[a]) * w for a, b, w in terms[cid]) + row[all_subsets[(cid,)]]) / N
+                          for cid in range(N)})
+        seconds.append(time.time() - t0)
+    return per_round, seconds
+
+
+def call_comfedsv(game, all_subsets, logger=None):
+    """One row of the ComFedSV utility matrix: every subset of the round's selected clients through the game
+    (one batched evaluation), plus the round's mask (compared_methods.py:47-62)."""
+    sets = list(powerset(game.selected_clients))
+    _prefetch(game, sets)
+    utilities = [np.zeros(len(all_subsets)) for _ in range(game.utility_dim)]
+    for S in sets:
+        u = game.eval_utility(S)
+        for i in range(game.utility_dim):
+            utilities[i][all_subsets[S]] = u[i]
+    return utilities, roundly_mask(game.selected_clients, all_subsets)
+

@@ -45,3 +45,21 @@ def test_non_participants_get_zero_and_module_reexports():
     for name in ("compute_utilities_lazy", "roundly_mask", "get_selection_dict", "compute_shapley_value_from_matrix",
                  "compute_shapley_value_groundtruth", "powerset", "ncr"):
         assert hasattr(ufs, name)
+
+
+@pytest.mark.parametrize("case", cases(), ids=lambda c: f"n{c['n']}")
+def test_comfedsv_matches_reference(case):
+    """compared_methods.py:17-73: per-round values from the utility matrix, and one matrix row through a game."""
+    from oracle.toy_games import ToyGame
+    from shapleyserver.fed_client_contribution import compared_methods as cm
+
+    n, T, part = case["n"], case["T"], case["participants"]
+    all_subsets = powerset(range(n))
+    per_round, seconds = cm.comfedsv(types.SimpleNamespace(num_clients=n, rounds=T), np.array(case["matrix"]), all_subsets)
+    assert len(per_round) == len(seconds) == T
+    for got, want in zip(per_round, case["comfedsv"]):
+        assert [got[c] for c in range(n)] == pytest.approx(want, abs=1e-14)
+    game = ToyGame(n, seed=n, selection=[c in part for c in range(n)])
+    util, mask = cm.call_comfedsv(game, all_subsets, None)
+    assert [u.tolist() for u in util] == case["call_comfedsv"]["utilities"]
+    assert mask.tolist() == case["call_comfedsv"]["mask"] == cm.roundly_mask(part, all_subsets).tolist()
