@@ -46,7 +46,9 @@ def parse_args():
     ap.add_argument("--val", type=int, default=10000)
     ap.add_argument("--coalition-batch", type=int, default=8)
     ap.add_argument("--image-chunk", type=int, default=128)
-    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "tf32", "f16x3", "f32"])
+    ap.add_argument("--precision", default="f16c8", choices=["f16c8", "f16x3", "f32", "f16", "bf16", "tf32"],
+                    help="f16c8 (default), f16x3, f32: parity modes (>= 99.9 %% top-1 agreement with fp32); "
+                         "f16, bf16, tf32: single-pass throughput modes outside that gate")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -220,7 +222,7 @@ def parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev):
     coalitions = list(powerset(range(n_c)))
     sv, preds, util = {}, {}, {}
     t0 = time.perf_counter()
-    gate = "f16x3" if a.precision in ("f16", "bf16", "tf32") else None   # the tensor-core mode that meets the top-1 gate
+    gate = "f16c8" if a.precision in ("f16", "bf16", "tf32") else None   # the tensor-core mode that meets the top-1 gate
     for prec in [x for x in (a.precision, gate, "f32") if x]:
         eng = CoalitionEngine(cfg, w0, deltas[:n_c].contiguous(), images, labels, precision=prec, coalition_batch=5,
                               image_chunk=min(32, n_img), device=dev, keep_logits=True)
@@ -463,13 +465,16 @@ def run_ours(a):
                 "traffic": traffic, "algorithmic_flops_per_launch": g_flops / max(g_n, 1),
                 "launches": int(g_n), "avg_launch_ms": g_ms / max(g_n, 1),
                 "share_of_step": g_ms / elapsed_ms}
-    if a.precision == "f16x3":  # every algorithmic product is three tensor-core passes (hi*hi + hi*lo + lo*hi)
-        roofline.update({"mma_passes": 3, "tensor_pipe_tflops": 3 * achieved, "tensor_pipe_frac": 3 * achieved / tensor_peak,
-                         "note": "achieved counts algorithmic flops; the tensor pipe executes 3x that (split-precision), "
-                                 "and the span includes the fp32 -> [hi|lo] operand split passes"})
+    if a.precision in ("f16x3", "f16c8"):
+        # every algorithmic product is 3 fp16 passes (f16x3) or 1 fp16 + 2 e4m3 passes at twice the rate (f16c8)
+        passes = 3.0 if a.precision == "f16x3" else 2.0
+        roofline.update({"mma_pass_equivalents": passes, "tensor_pipe_tflops": passes * achieved,
+                         "tensor_pipe_frac": passes * achieved / tensor_peak,
+                         "note": "achieved / frac count ALGORITHMIC flops against the bf16 dense peak; the tensor pipe is busy for "
+                                 f"{passes:g} fp16-pass equivalents per product (tensor_pipe_frac)"})
     a_ms, a_flops, a_n = timing["attention"]
     l_ms, l_bytes, l_n = timing["layernorm"]
-    es = 2 if a.precision in ("f16", "bf16") else 4
+    es = 2 if a.precision in ("f16", "bf16") else 4   # bytes per weight element over all planes
     agg_bytes = a.steps * (4.0 * lay.total * (N + 1) + (4.0 * lay.vec_size + es * lay.mat_size) * Cb)
     breakdown = {
         "gemm_ms": g_ms, "attention_ms": a_ms, "attention_tflops": a_flops / (a_ms / 1e3) / 1e12 if a_ms else None,

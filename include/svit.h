@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SVIT_ABI_VERSION 1
+#define SVIT_ABI_VERSION 2
 
 typedef void* svit_stream_t; /* cudaStream_t */
 
@@ -63,11 +63,25 @@ enum svit_precision {
   SVIT_PREC_TF32 = 1, /* fp32 storage, tcgen05 kind::tf32 */
   SVIT_PREC_BF16 = 2, /* bf16 operands, tcgen05 kind::f16 */
   SVIT_PREC_F16 = 3,  /* fp16 operands, tcgen05 kind::f16 (same rate as bf16, 3 more mantissa bits) */
-  SVIT_PREC_F16X3 = 4 /* fp32 storage; every GEMM operand is split into fp16 hi + lo halves and the product is
-                         three tcgen05 kind::f16 passes (hi*hi + hi*lo + lo*hi) into one fp32 accumulator:
-                         ~21 significant bits at a third of the f16 rate -- the tensor-core mode that meets
-                         the 99.9 % top-1 gate on random-init weights */
+  SVIT_PREC_F16X3 = 4, /* every GEMM operand is stored as fp16 hi + lo PLANES (SVIT_FMT_X3) and the product is
+                          three tcgen05 kind::f16 passes (hi*lo + lo*hi + hi*hi) into one fp32 accumulator:
+                          ~21 significant bits at a third of the f16 rate */
+  SVIT_PREC_F16C8 = 5  /* fp16 main pass + fp8 COMPENSATION passes (SVIT_FMT_C8): x*y ~ hi(x)*hi(y) [kind::f16]
+                          + 2^-15 (hi8(x)*lo8(y) + lo8(x)*hi8(y)) [kind::f8f6f4, e4m3, twice the f16 rate], the
+                          compensation summed first and folded in by the first f16 MMA's scale-input-d:
+                          ~16 significant bits (27x below one fp16 pass) for TWO f16-pass equivalents; attention
+                          runs in the X3 arithmetic.  Both split modes meet the 99.9 % top-1 gate on random-init
+                          weights; this one is the default */
 };
+
+/* Operand formats.  A PLAIN operand array is E elements of its svit_dtype.  The split formats are
+ * PACKED OPERAND ARRAYS of several planes inside one allocation of `alloc` elements (the plane pitch;
+ * alloc >= every element index used):
+ *   SVIT_FMT_X3: fp16 hi = fp16(x) at byte 0, fp16 lo = fp16(x - hi) at byte 2*alloc          (4 bytes / element)
+ *   SVIT_FMT_C8: fp16 hi at byte 0, e4m3 hi8 = e4m3(4 * hi) at byte 2*alloc,
+ *                e4m3 lo8 = e4m3(8192 * (x - hi)) at byte 3*alloc                              (4 bytes / element)
+ * Element (row, col) sits at the same index in every plane.  alloc must be a multiple of 16. */
+enum svit_operand_format { SVIT_FMT_PLAIN = 0, SVIT_FMT_X3 = 1, SVIT_FMT_C8 = 2 };
 
 typedef struct svit_vit_cfg {
   int32_t hidden, layers, heads, ff, image, patch, channels, n_cls;
@@ -127,6 +141,15 @@ int svit_aggregate_onto(const float* deltas, int64_t delta_stride, const float* 
                         const float* ratios, void* out, int64_t out_stride, int out_dtype, int64_t P, int N,
                         int C, svit_stream_t stream);
 
+/* The same aggregation written as a split-format packed operand array (the weight feed of SVIT_PREC_F16X3 /
+ * SVIT_PREC_F16C8): the value that is split is the fp32 two-rounding result above (w0 + sum, or base[c] + sum
+ * when `base` is given -- exactly one of w0 / base may be non-NULL, both NULL = zeros).
+ *   out  device packed operand array of out_alloc elements, element (c, p) at index out_off + c * out_stride + p
+ *        (out_off % 8 == 0) */
+int svit_aggregate_split(const float* deltas, int64_t delta_stride, const float* w0, const float* base,
+                         int64_t base_stride, const float* ratios, void* out, int64_t out_off, int64_t out_stride,
+                         int64_t out_alloc, int out_fmt, int64_t P, int N, int C, svit_stream_t stream);
+
 /* ---- forward ------------------------------------------------------------------------ */
 typedef struct svit_plan svit_plan; /* opaque: geometry, layout table, TMA descriptors */
 int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_coalitions, int max_images,
@@ -135,22 +158,28 @@ int svit_plan_destroy(svit_plan* plan);
 /* Bytes of caller-provided device workspace svit_forward_batched needs for (C, B) up to the
  * plan's maxima; 256-byte aligned. */
 int64_t svit_plan_workspace_bytes(const svit_plan* plan);
-/* dtype (svit_dtype) of the mat region / activations for this plan's precision. */
+/* dtype (svit_dtype) and format (svit_operand_format) of the mat region / patch matrix for this plan's
+ * precision (split formats: dtype is SVIT_F16, 4 bytes per element over all planes). */
 int svit_plan_operand_dtype(const svit_plan* plan);
+int svit_plan_operand_format(const svit_plan* plan);
 
-/* images [n, channels, image, image] fp32 (NCHW) -> patches [n * n_patches, channels*patch*patch]
- * in the plan's operand dtype, column order (channel, row, col) = the flattened conv kernel. */
-int svit_patchify(const svit_plan* plan, const float* images, void* patches, int64_t n,
-                  svit_stream_t stream);
+/* images [n, channels, image, image] fp32 (NCHW) -> rows [row0, row0 + n * n_patches) of the patch matrix
+ * [rows, channels*patch*patch] in the plan's operand format (split formats: a packed operand array of
+ * patches_alloc elements), column order (channel, row, col) = the flattened conv kernel. */
+int svit_patchify(const svit_plan* plan, const float* images, void* patches, int64_t patches_alloc, int64_t row0,
+                  int64_t n, svit_stream_t stream);
 
 /* logits[c * logits_stride + b * n_cls + k] for c < C, b < B: the ViT forward of image b under
  * the weights of coalition c.
- *   wvec  device [C, vec_stride] fp32          (vec region, from svit_aggregate)
- *   wmat  device [C, mat_stride] operand dtype (mat region, from svit_aggregate)
- *   patches device [B * n_patches, patch_dim] operand dtype (from svit_patchify), shared by all C */
+ *   wvec  device [C, vec_stride] fp32            (vec region, from svit_aggregate)
+ *   wmat  device [C, mat_stride] operand format  (mat region, from svit_aggregate / svit_aggregate_split;
+ *         split formats: packed operand array of wmat_alloc elements)
+ *   patches device [.., patch_dim] operand format (from svit_patchify; packed array of patches_alloc elements),
+ *         the B images start at row patches_row0; shared by all C */
 int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat,
-                         int64_t mat_stride, const void* patches, float* logits, int64_t logits_stride,
-                         int C, int B, void* workspace, size_t workspace_bytes, svit_stream_t stream);
+                         int64_t mat_stride, int64_t wmat_alloc, const void* patches, int64_t patches_alloc,
+                         int64_t patches_row0, float* logits, int64_t logits_stride, int C, int B, void* workspace,
+                         size_t workspace_bytes, svit_stream_t stream);
 
 /* Device-side timing of the forward by kernel class, for roofline reporting: between _begin and
  * _end every launch of svit_forward_batched on this plan is bracketed by CUDA events on its
@@ -188,30 +217,37 @@ typedef struct svit_epilogue {
 /* For g < G: out[g] = epilogue( A[g] (M x K, row-major) * B[g]^T (B[g] is N x K, row-major) ).
  * A, B in the operand dtype of `precision`; out_dtype is SVIT_F32 or that operand dtype.
  * Group strides may be 0 (operand shared by all groups).  M_out = M unless rows_in > 0. */
-/* SVIT_PREC_F16X3: A and B are PRE-SPLIT fp16 matrices [rows, 2K] = [hi | lo] per row (svit_split_f16),
- * strides in fp16 elements of that layout; K is the logical K and must be a multiple of 64. */
+/* SVIT_PREC_F16X3 / SVIT_PREC_F16C8: A and B are packed operand arrays (svit_split_operand) of exactly
+ * (a_gs ? G : 1) * M * K and G * N * K elements in the precision's format; out_dtype SVIT_F32 gives a plain fp32
+ * result, out_dtype SVIT_F16 a packed operand array of G * M_out * N elements in the same format (no rowvec /
+ * residual then). */
 int svit_gemm(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, void* out,
               int64_t out_gs, int out_dtype, int G, int M, int N, int K, const svit_epilogue* epi,
               svit_stream_t stream);
 
-/* out[g][r][0:K] = fp16(in[g][r][:]), out[g][r][K:2K] = fp16(in - hi): the operand format of
- * SVIT_PREC_F16X3.  in: fp32 [G][rows][K] with group stride in_gs (0 = one group); out: fp16
- * [G][rows][2K] contiguous.  K % 8 == 0; 16-byte aligned pointers. */
-int svit_split_f16(const float* in, int64_t in_gs, void* out, int G, int64_t rows, int K, svit_stream_t stream);
+/* fp32 array of `elems` elements -> packed operand array (out_fmt = SVIT_FMT_X3 / SVIT_FMT_C8) of out_alloc >=
+ * elems elements: what the producers of the forward (svit_aggregate_split, LayerNorm, the GEMM epilogues,
+ * attention) emit directly.  elems % 4 == 0, out_alloc % 16 == 0, 16-byte aligned pointers. */
+int svit_split_operand(const float* in, void* out, int64_t out_alloc, int out_fmt, int64_t elems,
+                       svit_stream_t stream);
 
 /* y[g, r, :] = LayerNorm(x[g, r, :]) * gamma[g] + beta[g]; x fp32 [G, rows, h] (row stride x_ld),
- * y in out_dtype, biased variance, eps as given (HF ViT: 1e-12). */
+ * y in out_dtype (out_fmt SVIT_FMT_PLAIN) or a packed operand array of out_alloc elements (split formats),
+ * biased variance, eps as given (HF ViT: 1e-12). */
 int svit_layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, const float* beta,
-                   int64_t param_gs, void* y, int64_t y_gs, int64_t y_ld, int out_dtype, int G,
-                   int64_t rows, int h, float eps, svit_stream_t stream);
+                   int64_t param_gs, void* y, int64_t y_gs, int64_t y_ld, int out_dtype, int out_fmt,
+                   int64_t out_alloc, int G, int64_t rows, int h, float eps, svit_stream_t stream);
 
 /* qkv [n_seq, T, 3h] (q | k | v, heads contiguous inside each) in `dtype` ->
  * ctx [n_seq, T, h] = softmax(q k^T / sqrt(d)) v per head, fp32 softmax. */
 int svit_attention(const void* qkv, void* ctx, int dtype, int64_t n_seq, int T, int heads, int head_dim,
                    svit_stream_t stream);
-/* The attention of SVIT_PREC_F16X3: fp32 qkv / ctx, head_dim 64, every product as fp16 hi*hi + hi*lo + lo*hi
- * on the tensor cores with fp32 accumulation and an fp32 softmax. */
-int svit_attention_f16x3(const float* qkv, float* ctx, int64_t n_seq, int T, int heads, svit_stream_t stream);
+/* The attention of the split precisions: qkv is an SVIT_FMT_X3 packed operand array of n_seq * T * 3h elements,
+ * ctx a packed operand array (ctx_fmt = SVIT_FMT_X3 / SVIT_FMT_C8) of n_seq * T * h elements.  Every product runs
+ * as fp16 hi*lo + lo*hi + hi*hi with fp32 accumulation (tcgen05 for head_dim 64 and 128 < T <= 216, CUDA cores
+ * otherwise), fp32 softmax. */
+int svit_attention_split(const void* qkv, void* ctx, int ctx_fmt, int64_t n_seq, int T, int heads, int head_dim,
+                         svit_stream_t stream);
 
 #ifdef __cplusplus
 }

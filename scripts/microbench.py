@@ -133,7 +133,7 @@ if __name__ == "__main__":
     if "attn32" in what:   # the register-tiled fp32 kernel of the f32 / tf32 modes, the split-precision one of f16x3
         bench_attn(C=2, dts=(torch.float32,))
         qkv = torch.randn(1024, 197, 2304, device="cuda") * 0.5
-        ms = timeit(lambda: ops.attention_f16x3(qkv, 12))
+        ms = timeit(lambda: ops.attention_split(qkv, 12))
         print(f"attention f16x3 n_seq=1024 T=197: {ms*1e3:8.1f} us  {4.0*1024*197*197*768/ms/1e9:7.1f} TFLOP/s", flush=True)
     if "ln" in what:
         bench_ln()

@@ -14,16 +14,27 @@ from . import build as _build
 
 # enums (mirror include/svit.h)
 F32, BF16, F16 = 0, 1, 2
-PREC_F32, PREC_TF32, PREC_BF16, PREC_F16, PREC_F16X3 = 0, 1, 2, 3, 4
+PREC_F32, PREC_TF32, PREC_BF16, PREC_F16, PREC_F16X3, PREC_F16C8 = 0, 1, 2, 3, 4, 5
 PRECISIONS = {"f32": PREC_F32, "fp32": PREC_F32, "tf32": PREC_TF32, "bf16": PREC_BF16, "f16": PREC_F16,
-              "fp16": PREC_F16, "f16x3": PREC_F16X3}
-OPERAND_DTYPE = {PREC_F32: F32, PREC_TF32: F32, PREC_BF16: BF16, PREC_F16: F16, PREC_F16X3: F32}
+              "fp16": PREC_F16, "f16x3": PREC_F16X3, "f16c8": PREC_F16C8}
+PRECISION_NAMES = {PREC_F32: "f32", PREC_TF32: "tf32", PREC_BF16: "bf16", PREC_F16: "f16", PREC_F16X3: "f16x3",
+                   PREC_F16C8: "f16c8"}
+# The precision a caller gets when it names none: the fastest mode that meets the parity gates of the path
+# (>= 99.9 % top-1 agreement with the fp32 reference, utilities within one sample): fp16 main pass + e4m3
+# compensation passes.  f16 / bf16 / tf32 are explicit opt-in throughput modes outside that tolerance.
+DEFAULT_PRECISION = "f16c8"
+OPERAND_DTYPE = {PREC_F32: F32, PREC_TF32: F32, PREC_BF16: BF16, PREC_F16: F16, PREC_F16X3: F16, PREC_F16C8: F16}
+FMT_PLAIN, FMT_X3, FMT_C8 = 0, 1, 2     # svit_operand_format
+OPERAND_FORMAT = {PREC_F32: FMT_PLAIN, PREC_TF32: FMT_PLAIN, PREC_BF16: FMT_PLAIN, PREC_F16: FMT_PLAIN,
+                  PREC_F16X3: FMT_X3, PREC_F16C8: FMT_C8}
+C8_HI_SCALE, C8_LO_SCALE = 4.0, 8192.0  # SVIT_C8_HI_SCALE / SVIT_C8_LO_SCALE (csrc/common.cuh)
 
 EXPORTS = [
     "svit_version", "svit_last_error", "svit_device_info", "svit_layout_sizes", "svit_layout_segment",
-    "svit_aggregate", "svit_aggregate_onto", "svit_plan_create", "svit_plan_destroy", "svit_plan_workspace_bytes",
-    "svit_plan_operand_dtype", "svit_patchify", "svit_forward_batched", "svit_score", "svit_gemm", "svit_split_f16",
-    "svit_layernorm", "svit_attention", "svit_attention_f16x3", "svit_plan_timing_begin", "svit_plan_timing_end",
+    "svit_aggregate", "svit_aggregate_onto", "svit_aggregate_split", "svit_plan_create", "svit_plan_destroy",
+    "svit_plan_workspace_bytes", "svit_plan_operand_dtype", "svit_plan_operand_format", "svit_patchify",
+    "svit_forward_batched", "svit_score", "svit_gemm", "svit_split_operand", "svit_layernorm", "svit_attention",
+    "svit_attention_split", "svit_plan_timing_begin", "svit_plan_timing_end",
 ]
 KERNEL_CLASSES = ("gemm", "attention", "layernorm", "forward")
 
@@ -90,18 +101,20 @@ def load() -> C.CDLL:
         "svit_layout_segment": (i32, [C.POINTER(VitCfgC), C.c_int32, C.POINTER(SegmentC)]),
         "svit_aggregate": (i32, [vp, i64, vp, vp, vp, i64, i32, i64, i32, i32, vp]),
         "svit_aggregate_onto": (i32, [vp, i64, vp, i64, vp, vp, i64, i32, i64, i32, i32, vp]),
+        "svit_aggregate_split": (i32, [vp, i64, vp, vp, i64, vp, vp, i64, i64, i64, i32, i64, i32, i32, vp]),
         "svit_plan_create": (i32, [C.POINTER(VitCfgC), i32, i32, i32, C.POINTER(vp)]),
         "svit_plan_destroy": (i32, [vp]),
         "svit_plan_workspace_bytes": (i64, [vp]),
         "svit_plan_operand_dtype": (i32, [vp]),
-        "svit_patchify": (i32, [vp, vp, vp, i64, vp]),
-        "svit_forward_batched": (i32, [vp, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp, C.c_size_t, vp]),
+        "svit_plan_operand_format": (i32, [vp]),
+        "svit_patchify": (i32, [vp, vp, vp, i64, i64, i64, vp]),
+        "svit_forward_batched": (i32, [vp, vp, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32, vp, C.c_size_t, vp]),
         "svit_score": (i32, [vp, i64, vp, i32, i64, i32, vp, vp, vp, i64, i32, vp]),
         "svit_gemm": (i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, C.POINTER(EpilogueC), vp]),
-        "svit_split_f16": (i32, [vp, i64, vp, i32, i64, i32, vp]),
-        "svit_layernorm": (i32, [vp, i64, i64, vp, vp, i64, vp, i64, i64, i32, i32, i64, i32, f32, vp]),
+        "svit_split_operand": (i32, [vp, vp, i64, i32, i64, vp]),
+        "svit_layernorm": (i32, [vp, i64, i64, vp, vp, i64, vp, i64, i64, i32, i32, i64, i32, i64, i32, f32, vp]),
         "svit_attention": (i32, [vp, vp, i32, i64, i32, i32, i32, vp]),
-        "svit_attention_f16x3": (i32, [vp, vp, i64, i32, i32, vp]),
+        "svit_attention_split": (i32, [vp, vp, i32, i64, i32, i32, i32, vp]),
         "svit_plan_timing_begin": (i32, [vp]),
         "svit_plan_timing_end": (i32, [vp, C.POINTER(TimingC)]),
     }

@@ -20,7 +20,7 @@ LIB = os.path.join(CSRC, "libsvit.so")
 STAMP = os.path.join(CSRC, ".libsvit.stamp")
 OBJDIR = os.path.join(CSRC, "build")
 
-SOURCES = ["layout.cu", "aggregate.cu", "score.cu", "elementwise.cu", "attention.cu", "attention_mma.cu", "attention_tc.cu", "tma_util.cu",
+SOURCES = ["layout.cu", "aggregate.cu", "score.cu", "elementwise.cu", "attention.cu", "attention_mma.cu", "attention_tc.cu", "attention_tc_split.cu", "tma_util.cu",
            "gemm_simt.cu", "gemm_tc.cu", "forward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

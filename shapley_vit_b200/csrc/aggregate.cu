@@ -23,6 +23,7 @@
 // order.  Algorithmic bytes per launch:
 //   4*P*(N+1) + sizeof(out)*P*C.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -105,23 +106,69 @@ __device__ __forceinline__ float2 accumulate(float2 acc, float r, float2 d) {
     return fma2(r, d, acc);
 }
 
-// 4 consecutive outputs, one streaming vector store (8 bytes for fp16/bf16, 16 for fp32)
+// Output element types.  OutX3 / OutC8 are the split operand formats (packed operand arrays, include/svit.h):
+// 4 bytes per element like fp32, and -- like fp32 -- the value that gets split is the reference's two-rounding
+// W_0 + sum (a 21-bit operand deserves the exact fp32 value; sizeof == 4 selects that arithmetic below).
+struct OutX3 { uint32_t tag; };
+struct OutC8 { uint32_t tag; };
+
+// 4 consecutive outputs at element index i of the output array: streaming vector stores
+// (8 bytes for fp16/bf16, 16 for fp32; one store per plane for the split formats)
 template <typename OutT> struct Store4;
 template <> struct Store4<float> {
-  static __device__ __forceinline__ void st(float* p, float2 a, float2 b) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4(a.x, a.y, b.x, b.y));
+  static __device__ __forceinline__ void st(void* out, int64_t, int64_t i, float2 a, float2 b) {
+    __stcs(reinterpret_cast<float4*>(static_cast<float*>(out) + i), make_float4(a.x, a.y, b.x, b.y));
   }
 };
 template <> struct Store4<__nv_bfloat16> {
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, float2 a, float2 b) {
-    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y)));
+  static __device__ __forceinline__ void st(void* out, int64_t, int64_t i, float2 a, float2 b) {
+    __stcs(reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(out) + i), make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(b.x, b.y)));
   }
 };
 template <> struct Store4<__half> {
-  static __device__ __forceinline__ void st(__half* p, float2 a, float2 b) {
-    __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_f16x2_sat(a.x, a.y), pack_f16x2_sat(b.x, b.y)));
+  static __device__ __forceinline__ void st(void* out, int64_t, int64_t i, float2 a, float2 b) {
+    __stcs(reinterpret_cast<uint2*>(static_cast<__half*>(out) + i), make_uint2(pack_f16x2_sat(a.x, a.y), pack_f16x2_sat(b.x, b.y)));
   }
 };
+template <> struct Store4<OutX3> {
+  static __device__ __forceinline__ void st(void* out, int64_t alloc, int64_t i, float2 a, float2 b) {
+    uint32_t h0, h1, l0, l1;
+    split_x3(a.x, a.y, h0, l0);
+    split_x3(b.x, b.y, h1, l1);
+    __stcs(reinterpret_cast<uint2*>(static_cast<__half*>(out) + i), make_uint2(h0, h1));
+    __stcs(reinterpret_cast<uint2*>(reinterpret_cast<__half*>(static_cast<char*>(out) + 2 * alloc) + i), make_uint2(l0, l1));
+  }
+};
+template <> struct Store4<OutC8> {
+  static __device__ __forceinline__ void st(void* out, int64_t alloc, int64_t i, float2 a, float2 b) {
+    uint32_t h0, h1;
+    uint16_t a0, a1, b0, b1;
+    split_c8(a.x, a.y, h0, a0, b0);
+    split_c8(b.x, b.y, h1, a1, b1);
+    __stcs(reinterpret_cast<uint2*>(static_cast<__half*>(out) + i), make_uint2(h0, h1));
+    __stcs(reinterpret_cast<uint32_t*>(static_cast<char*>(out) + 2 * alloc + i), (uint32_t)a0 | ((uint32_t)a1 << 16));
+    __stcs(reinterpret_cast<uint32_t*>(static_cast<char*>(out) + 3 * alloc + i), (uint32_t)b0 | ((uint32_t)b1 << 16));
+  }
+};
+// one output (ragged tails)
+template <typename OutT>
+__device__ __forceinline__ void store1(void* out, int64_t alloc, int64_t i, float v) {
+  if constexpr (std::is_same<OutT, OutX3>::value) {
+    uint32_t h, l;
+    split_x3(v, 0.f, h, l);
+    static_cast<uint16_t*>(out)[i] = (uint16_t)h;
+    reinterpret_cast<uint16_t*>(static_cast<char*>(out) + 2 * alloc)[i] = (uint16_t)l;
+  } else if constexpr (std::is_same<OutT, OutC8>::value) {
+    uint32_t h;
+    uint16_t a, b;
+    split_c8(v, 0.f, h, a, b);
+    static_cast<uint16_t*>(out)[i] = (uint16_t)h;
+    reinterpret_cast<uint8_t*>(out)[2 * alloc + i] = (uint8_t)a;
+    reinterpret_cast<uint8_t*>(out)[3 * alloc + i] = (uint8_t)b;
+  } else {
+    static_cast<OutT*>(out)[i] = Cvt<OutT>::from_f(v);
+  }
+}
 
 struct AggParams {
   const float* deltas;
@@ -129,7 +176,9 @@ struct AggParams {
   const float* w0;  // shared base row [P], may be null
   const float* base;  // per-coalition base rows [C, base_stride] fp32 (svit_aggregate_onto), exclusive with w0
   int64_t base_stride;
-  void* out;
+  void* out;          // output array (split formats: the main plane of the packed operand array)
+  int64_t out_off;    // element offset of this launch's first coalition row inside `out`
+  int64_t out_alloc;  // plane pitch in elements (split formats)
   int64_t out_stride;
   int64_t P;
   int N, C, stages;
@@ -258,12 +307,12 @@ __global__ void __launch_bounds__(kThreads, 3) aggregate_kernel(const __grid_con
   uint32_t parity = 0;
   for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
     const int len = tile_len(t);
-    OutT* outp = reinterpret_cast<OutT*>(p.out) + t * TILE;
+    const int64_t outp = p.out_off + t * TILE;  // element index of the tile in coalition row 0
 
     // the chunk's coalition rows: W_0 (or the per-coalition base) + acc, converted and stored
     auto write_chunk = [&](int ch) {
       if (len == TILE && !p.base) {  // full tile, shared W_0: whole vectors, the row pointer just advances
-        OutT* o = outp + (size_t)ch * kCChunk * p.out_stride;
+        int64_t o = outp + (int64_t)ch * kCChunk * p.out_stride;
         const int ncc = min(kCChunk, C - ch * kCChunk);
 #pragma unroll
         for (int cc = 0; cc < kCChunk; ++cc) {
@@ -271,8 +320,8 @@ __global__ void __launch_bounds__(kThreads, 3) aggregate_kernel(const __grid_con
             float2 v[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) v[q] = kFromW0 ? acc[cc][q] : add2(w[q], acc[cc][q]);
-            Store4<OutT>::st(o + ea, v[0], v[1]);
-            Store4<OutT>::st(o + eb, v[2], v[3]);
+            Store4<OutT>::st(p.out, p.out_alloc, o + ea, v[0], v[1]);
+            Store4<OutT>::st(p.out, p.out_alloc, o + eb, v[2], v[3]);
             o += p.out_stride;
           }
         }
@@ -288,17 +337,17 @@ __global__ void __launch_bounds__(kThreads, 3) aggregate_kernel(const __grid_con
           if (p.base) load_base(p.base + (size_t)c * p.base_stride + t * TILE, ea, eb, len, wb);
 #pragma unroll
           for (int q = 0; q < 4; ++q) v[q] = (kFromW0 && !p.base) ? acc[cc][q] : add2(wb[q], acc[cc][q]);
-          OutT* o = outp + (size_t)c * p.out_stride;
+          const int64_t o = outp + (int64_t)c * p.out_stride;
 #pragma unroll
           for (int grp = 0; grp < 2; ++grp) {
             const int e = grp ? eb : ea;
             if (e + 4 <= len) {
-              Store4<OutT>::st(o + e, v[2 * grp], v[2 * grp + 1]);
+              Store4<OutT>::st(p.out, p.out_alloc, o + e, v[2 * grp], v[2 * grp + 1]);
             } else {  // ragged tail: element-wise
               const float f[4] = {v[2 * grp].x, v[2 * grp].y, v[2 * grp + 1].x, v[2 * grp + 1].y};
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                if (e + q < len) o[e + q] = Cvt<OutT>::from_f(f[q]);
+                if (e + q < len) store1<OutT>(p.out, p.out_alloc, o + e + q, f[q]);
             }
           }
         }
@@ -436,20 +485,23 @@ namespace svit {
 namespace {
 
 int aggregate_impl(const char* who, const float* deltas, int64_t delta_stride, const float* w0, const float* base,
-                   int64_t base_stride, const float* ratios, void* out, int64_t out_stride, int out_dtype, int64_t P, int N,
-                   int C, svit_stream_t stream) {
+                   int64_t base_stride, const float* ratios, void* out, int64_t out_off, int64_t out_stride, int out_dtype,
+                   int out_fmt, int64_t out_alloc, int64_t P, int N, int C, svit_stream_t stream) {
   SVIT_CHECK_ARG(deltas && ratios && out, "%s: null pointer", who);
   SVIT_CHECK_ARG(P >= 0 && N >= 1 && N <= 64 && C >= 1 && C <= 256, "%s: P=%lld N=%d C=%d out of range", who, (long long)P, N,
                  C);
   SVIT_CHECK_ARG(out_dtype == SVIT_F32 || out_dtype == SVIT_BF16 || out_dtype == SVIT_F16, "%s: unknown out_dtype %d", who,
                  out_dtype);
+  SVIT_CHECK_ARG(out_fmt == SVIT_FMT_PLAIN || ((out_fmt == SVIT_FMT_X3 || out_fmt == SVIT_FMT_C8) && out_alloc % 16 == 0 &&
+                                               out_off % 8 == 0 && out_off >= 0 &&
+                                               out_alloc >= out_off + (int64_t)(C - 1) * out_stride + P),
+                 "%s: bad output format %d / plane pitch %lld", who, out_fmt, (long long)out_alloc);
   if (P == 0) return SVIT_OK;
   const int64_t p8 = round_up(P, 8);
   if (!aligned16(deltas) || !aligned16(out) || (w0 && !aligned16(w0)) || (base && !aligned16(base)) || delta_stride % 8 ||
       out_stride % 8 || delta_stride < p8 || out_stride < p8 || (base && (base_stride % 8 || base_stride < p8)))
     SVIT_FAIL(SVIT_ERR_ALIGN, "%s: pointers must be 16-byte aligned and strides multiples of 8 and >= round_up(P, 8)", who);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int es = dtype_size(out_dtype);
   // the ratio rows travel as kernel parameters: at most kMaxRatios floats per launch
   const int c_per_launch = (kMaxRatios / N) / kCChunk * kCChunk;
   for (int c0 = 0; c0 < C; c0 += c_per_launch) {
@@ -460,7 +512,9 @@ int aggregate_impl(const char* who, const float* deltas, int64_t delta_stride, c
     p.w0 = w0;
     p.base = base ? base + (size_t)c0 * base_stride : nullptr;
     p.base_stride = base_stride;
-    p.out = static_cast<char*>(out) + (size_t)c0 * out_stride * es;
+    p.out = out;
+    p.out_off = out_off + (int64_t)c0 * out_stride;
+    p.out_alloc = out_alloc;
     p.out_stride = out_stride;
     p.P = P;
     p.N = N;
@@ -473,11 +527,14 @@ int aggregate_impl(const char* who, const float* deltas, int64_t delta_stride, c
         if (r != 0.f) p.masks[(c / kCChunk) * N + j] |= 1u << (c % kCChunk);
       }
     int rc;
-    switch (out_dtype) {
-      case SVIT_F32: rc = dispatch_block<float>(p, s); break;
-      case SVIT_BF16: rc = dispatch_block<__nv_bfloat16>(p, s); break;
-      default: rc = dispatch_block<__half>(p, s); break;
-    }
+    if (out_fmt == SVIT_FMT_X3) rc = dispatch_block<OutX3>(p, s);
+    else if (out_fmt == SVIT_FMT_C8) rc = dispatch_block<OutC8>(p, s);
+    else
+      switch (out_dtype) {
+        case SVIT_F32: rc = dispatch_block<float>(p, s); break;
+        case SVIT_BF16: rc = dispatch_block<__nv_bfloat16>(p, s); break;
+        default: rc = dispatch_block<__half>(p, s); break;
+      }
     if (rc) return rc;
   }
   return SVIT_OK;
@@ -489,8 +546,8 @@ int aggregate_impl(const char* who, const float* deltas, int64_t delta_stride, c
 extern "C" int svit_aggregate(const float* deltas, int64_t delta_stride, const float* w0, const float* ratios,
                               void* out, int64_t out_stride, int out_dtype, int64_t P, int N, int C,
                               svit_stream_t stream) {
-  return svit::aggregate_impl("svit_aggregate", deltas, delta_stride, w0, nullptr, 0, ratios, out, out_stride, out_dtype, P, N,
-                              C, stream);
+  return svit::aggregate_impl("svit_aggregate", deltas, delta_stride, w0, nullptr, 0, ratios, out, 0, out_stride, out_dtype,
+                              SVIT_FMT_PLAIN, 0, P, N, C, stream);
 }
 
 extern "C" int svit_aggregate_onto(const float* deltas, int64_t delta_stride, const float* base, int64_t base_stride,
@@ -498,6 +555,17 @@ extern "C" int svit_aggregate_onto(const float* deltas, int64_t delta_stride, co
                                    int C, svit_stream_t stream) {
   using namespace svit;
   SVIT_CHECK_ARG(base != nullptr, "svit_aggregate_onto: base is null");
-  return aggregate_impl("svit_aggregate_onto", deltas, delta_stride, nullptr, base, base_stride, ratios, out, out_stride,
-                        out_dtype, P, N, C, stream);
+  return aggregate_impl("svit_aggregate_onto", deltas, delta_stride, nullptr, base, base_stride, ratios, out, 0, out_stride,
+                        out_dtype, SVIT_FMT_PLAIN, 0, P, N, C, stream);
+}
+
+extern "C" int svit_aggregate_split(const float* deltas, int64_t delta_stride, const float* w0, const float* base,
+                                    int64_t base_stride, const float* ratios, void* out, int64_t out_off,
+                                    int64_t out_stride, int64_t out_alloc, int out_fmt, int64_t P, int N, int C,
+                                    svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(out_fmt == SVIT_FMT_X3 || out_fmt == SVIT_FMT_C8, "svit_aggregate_split: out_fmt must be a split format");
+  SVIT_CHECK_ARG(!(w0 && base), "svit_aggregate_split: give w0 (shared) or base (per coalition), not both");
+  return aggregate_impl("svit_aggregate_split", deltas, delta_stride, w0, base, base_stride, ratios, out, out_off, out_stride,
+                        SVIT_F16, out_fmt, out_alloc, P, N, C, stream);
 }

@@ -447,9 +447,12 @@ extern "C" int svit_attention(const void* qkv, void* ctx, int dtype, int64_t n_s
   return attention(qkv, ctx, dtype, n_seq, T, heads, head_dim, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int svit_attention_f16x3(const float* qkv, float* ctx, int64_t n_seq, int T, int heads, svit_stream_t stream) {
+extern "C" int svit_attention_split(const void* qkv, void* ctx, int ctx_fmt, int64_t n_seq, int T, int heads, int head_dim,
+                                    svit_stream_t stream) {
   using namespace svit;
-  SVIT_CHECK_ARG(qkv && ctx, "svit_attention_f16x3: null pointer");
-  SVIT_CHECK_ARG(n_seq >= 0 && heads >= 1, "svit_attention_f16x3: bad sizes");
-  return attention_split(qkv, ctx, n_seq, T, heads, static_cast<cudaStream_t>(stream));
+  SVIT_CHECK_ARG(qkv && ctx, "svit_attention_split: null pointer");
+  SVIT_CHECK_ARG(n_seq >= 0 && heads >= 1, "svit_attention_split: bad sizes");
+  const int64_t h = (int64_t)heads * head_dim;
+  return attention_split(Operand{const_cast<void*>(qkv), SVIT_FMT_X3, n_seq * T * 3 * h}, Operand{ctx, ctx_fmt, n_seq * T * h},
+                         n_seq, T, heads, head_dim, false, static_cast<cudaStream_t>(stream));
 }

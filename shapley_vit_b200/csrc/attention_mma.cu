@@ -183,36 +183,38 @@ int dispatch_kt(const void* qkv, void* ctx, int64_t n_seq, int Tn, int heads, cu
   return launch_mma<T, 16>(qkv, ctx, n_seq, Tn, heads, stream);
 }
 
-// ---- split-precision variant (SVIT_PREC_F16X3): fp32 in, fp32 out -------------------------------
-// Same tiling as attention_mma_kernel, but Q, K, V arrive in fp32 and are staged as fp16 hi + lo
-// tiles (x = hi + lo to ~2^-22); every product runs hi*hi + hi*lo + lo*hi into the fp32
-// accumulators -- scores and P V both -- with P split in registers after the fp32 softmax.
-// ~21 significant bits end to end at three MMAs per tile: the attention of the f16x3 mode.
-// Only K and V are staged (hi + lo: 4 x 26 KB for T = 197), Q fragments are read from global memory and
-// split in registers, so two CTAs of four warps fit an SM and cover each other's staging phase and tail.
+// ---- split-precision variant (SVIT_PREC_F16X3 / F16C8): X3 planes in, split-format planes out ----
+// Same tiling as attention_mma_kernel.  Q, K, V arrive as fp16 hi + lo planes (the QKV GEMM's epilogue
+// emits them: x = hi + lo to ~2^-22); every product runs lo*hi + hi*lo + hi*hi into the fp32
+// accumulators -- scores and P V both -- with P split in registers after the fp32 softmax, and the
+// context goes out in the consumer GEMM's operand format (X3 or C8 planes).
+// ~21 significant bits end to end at three MMAs per tile.  This is the warp-level (mma.sync) kernel for
+// the shapes the tcgen05 kernel (attention_tc_split.cu) does not take: T <= 128 or T > 216.
+// Only K and V are staged (hi + lo: 4 x 26 KB for T = 197), Q fragments come straight from global memory,
+// so two CTAs of four warps fit an SM and cover each other's staging phase and tail.
 constexpr int kWarps3 = 4;
 
-__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  hi = pack_f16x2_sat(x, y);
-  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-  lo = pack_f16x2_sat(x - hf.x, y - hf.y);
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) { split_x3(x, y, hi, lo); }
+
+template <int FMT>
+__device__ __forceinline__ void store2_planes(const Operand& o, int64_t i, float a, float b) {
+  if constexpr (FMT == SVIT_FMT_X3) {
+    uint32_t h, l;
+    split_x3(a, b, h, l);
+    *reinterpret_cast<uint32_t*>(static_cast<__half*>(o.base) + i) = h;
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<__half*>(o.aux1()) + i) = l;
+  } else {
+    uint32_t h;
+    uint16_t h8, l8;
+    split_c8(a, b, h, h8, l8);
+    *reinterpret_cast<uint32_t*>(static_cast<__half*>(o.base) + i) = h;
+    *reinterpret_cast<uint16_t*>(o.aux1() + i) = h8;
+    *reinterpret_cast<uint16_t*>(o.aux2() + i) = l8;
+  }
 }
 
-__device__ __forceinline__ void split8(const float* __restrict__ src, unsigned char* hi_tile, unsigned char* lo_tile,
-                                       uint32_t off) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-  uint4 hi, lo;
-  split2(a.x, a.y, hi.x, lo.x);
-  split2(a.z, a.w, hi.y, lo.y);
-  split2(b.x, b.y, hi.z, lo.z);
-  split2(b.z, b.w, hi.w, lo.w);
-  *reinterpret_cast<uint4*>(hi_tile + off) = hi;
-  *reinterpret_cast<uint4*>(lo_tile + off) = lo;
-}
-
-template <int KT>
-__global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const float* __restrict__ qkv, float* __restrict__ ctx,
-                                                                        int Tn, int heads) {
+template <int KT, int OFMT>
+__global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const Operand qkv, const Operand ctx, int Tn, int heads) {
   constexpr int TP = KT * 16;
   constexpr int TILE = TP * 128;
   extern __shared__ __align__(128) unsigned char att_raw[];
@@ -220,21 +222,23 @@ __global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const flo
   const int h = heads * kD;
   const int64_t seq = blockIdx.x;
   const int head = blockIdx.y;
-  const float* base = qkv + seq * (int64_t)Tn * 3 * h + head * kD;
+  const __half* qh = static_cast<const __half*>(qkv.base) + seq * (int64_t)Tn * 3 * h + head * kD;
+  const __half* ql = reinterpret_cast<const __half*>(qkv.aux1()) + seq * (int64_t)Tn * 3 * h + head * kD;
   const int tid = threadIdx.x;
 
   for (int i = tid; i < TP * 8; i += kWarps3 * 32) {  // rows >= Tn are zero
     const int row = i >> 3, chunk = i & 7;
     const uint32_t off = tile_off(row, chunk);
+    uint4 v[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     if (row < Tn) {
-      const float* src = base + (size_t)row * 3 * h + chunk * 8;
-      split8(src + h, Kh, Kh + TILE, off);
-      split8(src + 2 * h, Kh + 2 * TILE, Kh + 3 * TILE, off);
-    } else {
-      const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) *reinterpret_cast<uint4*>(Kh + m * TILE + off) = z;
+      const size_t src = (size_t)row * 3 * h + chunk * 8;
+      v[0] = __ldg(reinterpret_cast<const uint4*>(qh + src + h));
+      v[1] = __ldg(reinterpret_cast<const uint4*>(ql + src + h));
+      v[2] = __ldg(reinterpret_cast<const uint4*>(qh + src + 2 * h));
+      v[3] = __ldg(reinterpret_cast<const uint4*>(ql + src + 2 * h));
     }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) *reinterpret_cast<uint4*>(Kh + m * TILE + off) = v[m];
   }
   __syncthreads();
 
@@ -253,20 +257,18 @@ __global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const flo
 #pragma unroll
     for (int ks = 0; ks < kD / 16; ++ks) {
       // A fragments of m16n8k16 straight from global memory: rows g / g + 8, columns 2t, 2t+1 (+8) of the k-block
-      uint32_t ah[4], al[4];
+      uint32_t ah[4] = {0, 0, 0, 0}, al[4] = {0, 0, 0, 0};
       {
-        const float* qa = base + (size_t)(r0 + g) * 3 * h + ks * 16 + 2 * t;
-        const float* qb = qa + (size_t)8 * 3 * h;
-        const float2 z = make_float2(0.f, 0.f);
-        const bool va = r0 + g < Tn, vb = r0 + g + 8 < Tn;
-        const float2 q0 = va ? __ldg(reinterpret_cast<const float2*>(qa)) : z;
-        const float2 q1 = vb ? __ldg(reinterpret_cast<const float2*>(qb)) : z;
-        const float2 q2 = va ? __ldg(reinterpret_cast<const float2*>(qa + 8)) : z;
-        const float2 q3 = vb ? __ldg(reinterpret_cast<const float2*>(qb + 8)) : z;
-        split2(q0.x, q0.y, ah[0], al[0]);
-        split2(q1.x, q1.y, ah[1], al[1]);
-        split2(q2.x, q2.y, ah[2], al[2]);
-        split2(q3.x, q3.y, ah[3], al[3]);
+        const size_t qa = (size_t)(r0 + g) * 3 * h + ks * 16 + 2 * t;
+        const size_t qb = qa + (size_t)8 * 3 * h;
+        if (r0 + g < Tn) {
+          ah[0] = __ldg(reinterpret_cast<const uint32_t*>(qh + qa)), al[0] = __ldg(reinterpret_cast<const uint32_t*>(ql + qa));
+          ah[2] = __ldg(reinterpret_cast<const uint32_t*>(qh + qa + 8)), al[2] = __ldg(reinterpret_cast<const uint32_t*>(ql + qa + 8));
+        }
+        if (r0 + g + 8 < Tn) {
+          ah[1] = __ldg(reinterpret_cast<const uint32_t*>(qh + qb)), al[1] = __ldg(reinterpret_cast<const uint32_t*>(ql + qb));
+          ah[3] = __ldg(reinterpret_cast<const uint32_t*>(qh + qb + 8)), al[3] = __ldg(reinterpret_cast<const uint32_t*>(ql + qb + 8));
+        }
       }
 #pragma unroll
       for (int np = 0; np < KT; ++np) {
@@ -336,24 +338,92 @@ __global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const flo
       }
     }
     const int ra = r0 + g, rb = r0 + g + 8;
-    float* out = ctx + seq * (int64_t)Tn * h + head * kD + 2 * t;
+    const int64_t out = seq * (int64_t)Tn * h + head * kD + 2 * t;
 #pragma unroll
     for (int dt = 0; dt < kD / 8; ++dt) {
-      if (ra < Tn) *reinterpret_cast<float2*>(out + (size_t)ra * h + dt * 8) = make_float2(O[dt][0], O[dt][1]);
-      if (rb < Tn) *reinterpret_cast<float2*>(out + (size_t)rb * h + dt * 8) = make_float2(O[dt][2], O[dt][3]);
+      if (ra < Tn) store2_planes<OFMT>(ctx, out + (int64_t)ra * h + dt * 8, O[dt][0], O[dt][1]);
+      if (rb < Tn) store2_planes<OFMT>(ctx, out + (int64_t)rb * h + dt * 8, O[dt][2], O[dt][3]);
     }
   }
 }
 
-template <int KT>
-int launch_split(const float* qkv, float* ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
+// ---- the [CLS] query alone (last encoder layer): one warp per (sequence, head), fp32 CUDA-core arithmetic on
+// the reconstructed hi + lo values; ctx_cls [n_seq, h] in the consumer GEMM's split format
+template <int OFMT>
+__global__ void __launch_bounds__(256) attention_cls_split_kernel(const Operand qkv, const Operand ctx, int Tn, int heads,
+                                                                  int64_t n_items) {
+  __shared__ float q_s[8][kD];
+  __shared__ float p_s[8][256];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = blockIdx.x * 8LL + w;
+  if (item >= n_items) return;
+  const int64_t seq = item / heads;
+  const int head = (int)(item % heads);
+  const int h = heads * kD;
+  const int64_t base = seq * (int64_t)Tn * 3 * h + head * kD;
+  for (int d = lane; d < kD; d += 32) q_s[w][d] = load_x3(qkv, base + d);
+  __syncwarp();
+  constexpr int KPL = 8;  // keys per lane: T <= 256
+  float s[KPL];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < KPL; ++k) {
+    const int j = lane + k * 32;
+    s[k] = -INFINITY;
+    if (j < Tn) {
+      const int64_t kb = base + (int64_t)j * 3 * h + h;
+      float dot = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < kD; ++d) dot = fmaf(q_s[w][d], load_x3(qkv, kb + d), dot);
+      s[k] = dot * 0.125f;
+      m = fmaxf(m, s[k]);
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KPL; ++k) {
+    s[k] = lane + k * 32 < Tn ? expf(s[k] - m) : 0.f;
+    sum += s[k];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int k = 0; k < KPL; ++k) p_s[w][lane + k * 32] = s[k] * inv;
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;  // the lane owns two consecutive channels
+  const int64_t vb = base + 2 * h + lane * 2;
+  for (int j = 0; j < Tn; ++j) {
+    const float pj = p_s[w][j];
+    o0 = fmaf(pj, load_x3(qkv, vb + (int64_t)j * 3 * h), o0);
+    o1 = fmaf(pj, load_x3(qkv, vb + (int64_t)j * 3 * h + 1), o1);
+  }
+  store2_planes<OFMT>(ctx, seq * (int64_t)h + head * kD + lane * 2, o0, o1);
+}
+
+template <int KT, int OFMT>
+int launch_split(const Operand& qkv, const Operand& ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
   const size_t smem = (size_t)4 * KT * 16 * 128;
-  auto kern = attention_split_kernel<KT>;
+  auto kern = attention_split_kernel<KT, OFMT>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)n_seq, heads);
   kern<<<grid, kWarps3 * 32, smem, stream>>>(qkv, ctx, Tn, heads);
   SVIT_LAUNCH_CHECK("attention_split_kernel");
   return SVIT_OK;
+}
+
+template <int OFMT>
+int dispatch_split(const Operand& qkv, const Operand& ctx, int64_t n_seq, int Tn, int heads, bool cls_only, cudaStream_t stream) {
+  if (cls_only) {
+    const int64_t items = n_seq * heads;
+    attention_cls_split_kernel<OFMT><<<(unsigned)((items + 7) / 8), 256, 0, stream>>>(qkv, ctx, Tn, heads, items);
+    SVIT_LAUNCH_CHECK("attention_cls_split_kernel");
+    return SVIT_OK;
+  }
+  if (Tn <= 16) return launch_split<1, OFMT>(qkv, ctx, n_seq, Tn, heads, stream);
+  if (Tn <= 64) return launch_split<4, OFMT>(qkv, ctx, n_seq, Tn, heads, stream);
+  if (Tn <= 208) return launch_split<13, OFMT>(qkv, ctx, n_seq, Tn, heads, stream);
+  return launch_split<16, OFMT>(qkv, ctx, n_seq, Tn, heads, stream);
 }
 
 }  // namespace
@@ -369,16 +439,24 @@ int attention_mma(const void* qkv, void* ctx, int dtype, int64_t n_seq, int Tn, 
   SVIT_FAIL(SVIT_ERR_ARG, "attention_mma: dtype %d is not a 16-bit type", dtype);
 }
 
-// fp32 qkv / ctx, head_dim 64, T <= 256: split-precision tensor-core attention (SVIT_PREC_F16X3)
-int attention_split(const float* qkv, float* ctx, int64_t n_seq, int Tn, int heads, cudaStream_t stream) {
+// X3 qkv planes, split-format ctx planes, head_dim 64, T <= 256: the attention of the split precisions
+int attention_split(const Operand& qkv, const Operand& ctx, int64_t n_seq, int Tn, int heads, int head_dim, bool cls_only,
+                    cudaStream_t stream) {
   if (n_seq == 0) return SVIT_OK;
   SVIT_CHECK_ARG(Tn >= 1 && Tn <= 256, "attention: T=%d out of range (1..256)", Tn);
   SVIT_CHECK_ARG(n_seq <= 0x7fffffff, "attention: too many sequences");
-  if (!aligned16(qkv) || !aligned16(ctx)) SVIT_FAIL(SVIT_ERR_ALIGN, "attention: qkv/ctx must be 16-byte aligned");
-  if (Tn <= 16) return launch_split<1>(qkv, ctx, n_seq, Tn, heads, stream);
-  if (Tn <= 64) return launch_split<4>(qkv, ctx, n_seq, Tn, heads, stream);
-  if (Tn <= 208) return launch_split<13>(qkv, ctx, n_seq, Tn, heads, stream);
-  return launch_split<16>(qkv, ctx, n_seq, Tn, heads, stream);
+  if (head_dim != kD) SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "attention_split: head_dim %d (the split precisions take head_dim 64)", head_dim);
+  SVIT_CHECK_ARG(qkv.fmt == SVIT_FMT_X3 && (ctx.fmt == SVIT_FMT_X3 || ctx.fmt == SVIT_FMT_C8),
+                 "attention_split: qkv must be X3 planes and ctx X3 or C8 planes");
+  if (!aligned16(qkv.base) || !aligned16(ctx.base) || qkv.alloc % 16 || ctx.alloc % 16)
+    SVIT_FAIL(SVIT_ERR_ALIGN, "attention: qkv/ctx must be 16-byte aligned with plane pitches multiples of 16");
+  static const bool no_tc = [] {
+    const char* e = getenv("SVIT_ATTENTION_MMA_SYNC");
+    return e && e[0] == '1';
+  }();
+  if (!cls_only && !no_tc && Tn > 128 && attention_split_tc_fits(Tn)) return attention_split_tc(qkv, ctx, n_seq, Tn, heads, stream);
+  return ctx.fmt == SVIT_FMT_X3 ? dispatch_split<SVIT_FMT_X3>(qkv, ctx, n_seq, Tn, heads, cls_only, stream)
+                                : dispatch_split<SVIT_FMT_C8>(qkv, ctx, n_seq, Tn, heads, cls_only, stream);
 }
 
 }  // namespace svit

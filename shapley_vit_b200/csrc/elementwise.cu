@@ -10,9 +10,22 @@
 namespace svit {
 namespace {
 
-// ---- patchify: NCHW fp32 images -> [n * np, C*ps*ps] rows in the operand dtype ------------
+// Where a kernel's 16-bit / fp32 results go: a plain array of T, or the planes of a split-format packed
+// operand array (include/svit.h).  i = element index, a multiple of 4.
 template <typename T>
-__global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ out, int64_t n, int C, int H, int ps) {
+struct PlainOut {
+  T* y;
+  __device__ __forceinline__ void st4(int64_t i, float a, float b, float c, float d) const { store4<T>(y + i, a, b, c, d); }
+};
+template <int FMT>
+struct SplitOut {
+  Operand o;
+  __device__ __forceinline__ void st4(int64_t i, float a, float b, float c, float d) const { store4_planes<FMT>(o, i, a, b, c, d); }
+};
+
+// ---- patchify: NCHW fp32 images -> [n * np, C*ps*ps] rows in the operand format ------------
+template <class Out>
+__global__ void patchify_kernel(const float* __restrict__ img, const Out out, int64_t off, int64_t n, int C, int H, int ps) {
   const int gw = H / ps;                       // patches per side
   const int pd = C * ps * ps;                  // row length
   const int q_per_row = pd / 4;                // float4 groups per output row
@@ -26,18 +39,18 @@ __global__ void patchify_kernel(const float* __restrict__ img, T* __restrict__ o
     const int p = (int)(row % (gw * gw)), py = p / gw, px = p % gw;
     const float4 v = *reinterpret_cast<const float4*>(
         img + ((im * C + c) * H + (py * ps + ky)) * (int64_t)H + px * ps + kx);
-    store4<T>(out + row * pd + col, v.x, v.y, v.z, v.w);
+    out.st4(off + row * pd + col, v.x, v.y, v.z, v.w);
   }
 }
 
 // ---- LayerNorm: one warp per row, fp32 statistics, two-pass variance ----------------------
 constexpr int kLnMaxVec = 8;  // h <= 1024
 
-template <typename T>
+template <class Out>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t x_gs, int64_t x_ld,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, int64_t param_gs,
-                                                        T* __restrict__ y, int64_t y_gs, int64_t y_ld, int64_t rows,
+                                                        const Out y, int64_t y_gs, int64_t y_ld, int64_t rows,
                                                         int64_t total_rows, int h, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t r = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -67,14 +80,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)h + eps);
   const float* gm = gamma + g * param_gs;
   const float* bt = beta + g * param_gs;
-  T* yr = y + g * y_gs + rr * y_ld;
+  const int64_t yr = g * y_gs + rr * y_ld;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
     const int idx = lane + i * 32;
     if (idx < h4) {
       const float4 gg = reinterpret_cast<const float4*>(gm)[idx], bb = reinterpret_cast<const float4*>(bt)[idx];
-      store4<T>(yr + idx * 4, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
-                (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+      y.st4(yr + idx * 4, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+            (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
     }
   }
 }
@@ -84,11 +97,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // incrementally instead of by a 64-bit division per row.  Fewer instructions per row than the generic
 // kernel -- which matters inside a forward step, where the GEMMs hold the SM clock at the power cap and
 // this kernel's issue rate, not HBM, paces it.
-template <typename T, int VPL>
+template <class Out, int VPL>
 __global__ void __launch_bounds__(256) layernorm_fixed_kernel(const float* __restrict__ x, int64_t x_gs, int64_t x_ld,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, int64_t param_gs,
-                                                              T* __restrict__ y, int64_t y_gs, int64_t y_ld, int64_t rows,
+                                                              const Out y, int64_t y_gs, int64_t y_ld, int64_t rows,
                                                               int64_t total_rows, float eps) {
   constexpr int H = VPL * 128;
   const int lane = threadIdx.x & 31;
@@ -113,12 +126,12 @@ __global__ void __launch_bounds__(256) layernorm_fixed_kernel(const float* __res
     const float rstd = 1.0f / sqrtf(warp_sum(sq) / (float)H + eps);
     const float4* gm = reinterpret_cast<const float4*>(gamma + g * param_gs) + lane;  // L1 hits: shared by the coalition's rows
     const float4* bt = reinterpret_cast<const float4*>(beta + g * param_gs) + lane;
-    T* yr = y + g * y_gs + rr * y_ld + lane * 4;
+    const int64_t yr = g * y_gs + rr * y_ld + lane * 4;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const float4 gg = gm[i * 32], bb = bt[i * 32];
-      store4<T>(yr + i * 128, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
-                (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
+      y.st4(yr + i * 128, (v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y,
+            (v[i].z - mean) * rstd * gg.z + bb.z, (v[i].w - mean) * rstd * gg.w + bb.w);
     }
     rr += nwarps;
     while (rr >= rows) rr -= rows, ++g;
@@ -201,67 +214,74 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ X, 
 
 }  // namespace
 
-// ---- fp32 -> [hi | lo] fp16 rows: the operand format of SVIT_PREC_F16X3 ---------------------------
-// x = hi + lo + O(2^-22 |x|) with hi = fp16(x), lo = fp16(x - hi) (x - hi is exact in fp32).
-__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ in, int64_t in_gs,
-                                                        __half* __restrict__ out, int64_t rows, int K, int64_t total) {
-  const int kv = K >> 3;  // 8-element pieces per row
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / kv;  // row over all groups
-    const int c = (int)(i - row * kv) << 3;
-    const int64_t g = row / rows, r = row - g * rows;
-    const float4* src = reinterpret_cast<const float4*>(in + g * in_gs + r * K + c);
-    const float4 a = __ldg(src), b = __ldg(src + 1);
-    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    __half2 hi[4], lo[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      hi[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-      const float2 hf = __half22float2(hi[j]);
-      lo[j] = __floats2half2_rn(__fsub_rn(x[2 * j], hf.x), __fsub_rn(x[2 * j + 1], hf.y));
-    }
-    __half* dst = out + row * (2 * (int64_t)K) + c;
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(dst + K) = *reinterpret_cast<const uint4*>(lo);
+// ---- fp32 -> split-format packed operand array (SVIT_FMT_X3 / SVIT_FMT_C8) -----------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) split_operand_kernel(const float* __restrict__ in, const Operand out, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in) + i);
+    store4_planes<FMT>(out, 4 * i, a.x, a.y, a.z, a.w);
   }
 }
 
-int patchify(int dtype, const float* images, void* patches, int64_t n, int C, int H, int ps, cudaStream_t stream) {
+// run `body(out_policy)` with the output policy of (dtype, operand format)
+#define SVIT_WITH_OUT(y, body)                                                              \
+  do {                                                                                      \
+    if ((y).fmt == SVIT_FMT_X3) {                                                           \
+      const SplitOut<SVIT_FMT_X3> out_{(y)};                                                \
+      body;                                                                                 \
+    } else if ((y).fmt == SVIT_FMT_C8) {                                                    \
+      const SplitOut<SVIT_FMT_C8> out_{(y)};                                                \
+      body;                                                                                 \
+    } else if (out_dtype == SVIT_F32) {                                                     \
+      const PlainOut<float> out_{static_cast<float*>((y).base)};                            \
+      body;                                                                                 \
+    } else if (out_dtype == SVIT_BF16) {                                                    \
+      const PlainOut<__nv_bfloat16> out_{static_cast<__nv_bfloat16*>((y).base)};            \
+      body;                                                                                 \
+    } else if (out_dtype == SVIT_F16) {                                                     \
+      const PlainOut<__half> out_{static_cast<__half*>((y).base)};                          \
+      body;                                                                                 \
+    } else {                                                                                \
+      SVIT_FAIL(SVIT_ERR_ARG, "bad output dtype %d", out_dtype);                            \
+    }                                                                                       \
+  } while (0)
+
+template <class Out>
+void launch_patchify(const Out& out, int grid, int block, const float* images, int64_t off, int64_t n, int C, int H, int ps,
+                     cudaStream_t stream) {
+  patchify_kernel<Out><<<grid, block, 0, stream>>>(images, out, off, n, C, H, ps);
+}
+
+// rows start at element offset `off` of the patch matrix
+int patchify_at(int out_dtype, const float* images, const Operand& patches, int64_t off, int64_t n, int C, int H, int ps,
+                cudaStream_t stream) {
   if (n == 0) return SVIT_OK;
   SVIT_CHECK_ARG(ps % 4 == 0 && H % ps == 0, "patchify: patch must be a multiple of 4 and divide the image");
   const int64_t total = n * (H / ps) * (H / ps) * (int64_t)(C * ps * ps / 4);
   const int block = 256;
   const int grid = (int)std::min<int64_t>((total + block - 1) / block, (int64_t)sm_count() * 16);
-  switch (dtype) {
-    case SVIT_F32: patchify_kernel<float><<<grid, block, 0, stream>>>(images, (float*)patches, n, C, H, ps); break;
-    case SVIT_BF16:
-      patchify_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(images, (__nv_bfloat16*)patches, n, C, H, ps);
-      break;
-    case SVIT_F16: patchify_kernel<__half><<<grid, block, 0, stream>>>(images, (__half*)patches, n, C, H, ps); break;
-    default: SVIT_FAIL(SVIT_ERR_ARG, "patchify: bad dtype %d", dtype);
-  }
+  SVIT_WITH_OUT(patches, launch_patchify(out_, grid, block, images, off, n, C, H, ps, stream));
   SVIT_LAUNCH_CHECK("patchify_kernel");
   return SVIT_OK;
 }
 
-int split_f16(const float* in, int64_t in_gs, void* out, int G, int64_t rows, int K, cudaStream_t stream) {
-  SVIT_CHECK_ARG(K % 8 == 0 && in_gs % 4 == 0, "split_f16: K and the group stride must be multiples of 8 / 4");
-  const int64_t total = (int64_t)G * rows * (K / 8);
-  if (total == 0) return SVIT_OK;
+int split_operand(const float* in, const Operand& out, int64_t elems, cudaStream_t stream) {
+  SVIT_CHECK_ARG(elems % 4 == 0 && out.alloc >= elems && out.alloc % 16 == 0, "split_operand: elems %% 4 and alloc %% 16 must be 0, alloc >= elems");
+  SVIT_CHECK_ARG(out.fmt == SVIT_FMT_X3 || out.fmt == SVIT_FMT_C8, "split_operand: out must be a split format");
+  if (elems == 0) return SVIT_OK;
+  const int64_t n4 = elems / 4;
   const int block = 256;
-  const int grid = (int)std::min<int64_t>((total + block - 1) / block, (int64_t)sm_count() * 16);
-  split_f16_kernel<<<grid, block, 0, stream>>>(in, in_gs, static_cast<__half*>(out), rows, K, total);
-  SVIT_LAUNCH_CHECK("split_f16_kernel");
+  const int grid = (int)std::min<int64_t>((n4 + block - 1) / block, (int64_t)sm_count() * 16);
+  if (out.fmt == SVIT_FMT_X3) split_operand_kernel<SVIT_FMT_X3><<<grid, block, 0, stream>>>(in, out, n4);
+  else split_operand_kernel<SVIT_FMT_C8><<<grid, block, 0, stream>>>(in, out, n4);
+  SVIT_LAUNCH_CHECK("split_operand_kernel");
   return SVIT_OK;
 }
 
-int layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, const float* beta, int64_t param_gs,
-              void* y, int64_t y_gs, int64_t y_ld, int out_dtype, int G, int64_t rows, int h, float eps,
-              cudaStream_t stream) {
-  SVIT_CHECK_ARG(h % 4 == 0 && h <= kLnMaxVec * 128, "layernorm: h=%d must be a multiple of 4 and <= 1024", h);
-  SVIT_CHECK_ARG(x_ld % 4 == 0 && y_ld % 4 == 0 && x_gs % 4 == 0 && param_gs % 4 == 0, "layernorm: strides must be multiples of 4");
+template <class Out>
+int launch_layernorm(const Out& out, const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, const float* beta,
+                     int64_t param_gs, int64_t y_gs, int64_t y_ld, int G, int64_t rows, int h, float eps, cudaStream_t stream) {
   const int64_t total = (int64_t)G * rows;
-  if (total == 0) return SVIT_OK;
   const int wpb = 8;
   static const bool generic_only = [] {  // SVIT_LN_GENERIC=1: the bounds-checked kernel for every h (A/B)
     const char* e = getenv("SVIT_LN_GENERIC");
@@ -270,45 +290,34 @@ int layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, co
   if ((h == 768 || h == 1024) && !generic_only) {  // whole warps: the persistent fixed-size kernel
     int per_sm = 0;  // one resident wave of persistent warps
     if (h == 768) {
-      SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_fixed_kernel<__half, 6>, wpb * 32, 0));
+      SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_fixed_kernel<Out, 6>, wpb * 32, 0));
     } else {
-      SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_fixed_kernel<float, 8>, wpb * 32, 0));
+      SVIT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_fixed_kernel<Out, 8>, wpb * 32, 0));
     }
     if (per_sm < 1) per_sm = 1;
     const unsigned pgrid = (unsigned)std::min<int64_t>((total + wpb - 1) / wpb, (int64_t)sm_count() * per_sm);
-#define SVIT_LNF(T, V)                                                                                                 \
-  layernorm_fixed_kernel<T, V><<<pgrid, wpb * 32, 0, stream>>>(x, x_gs, x_ld, gamma, beta, param_gs, (T*)y, y_gs, y_ld, \
-                                                               rows, total, eps)
-#define SVIT_LNH(T)          \
-  if (h == 768) {            \
-    SVIT_LNF(T, 6);          \
-  } else {                   \
-    SVIT_LNF(T, 8);          \
-  }
-    switch (out_dtype) {
-      case SVIT_F32: SVIT_LNH(float); break;
-      case SVIT_BF16: SVIT_LNH(__nv_bfloat16); break;
-      case SVIT_F16: SVIT_LNH(__half); break;
-      default: SVIT_FAIL(SVIT_ERR_ARG, "layernorm: bad dtype %d", out_dtype);
-    }
-#undef SVIT_LNH
-#undef SVIT_LNF
+    if (h == 768)
+      layernorm_fixed_kernel<Out, 6><<<pgrid, wpb * 32, 0, stream>>>(x, x_gs, x_ld, gamma, beta, param_gs, out, y_gs, y_ld, rows, total, eps);
+    else
+      layernorm_fixed_kernel<Out, 8><<<pgrid, wpb * 32, 0, stream>>>(x, x_gs, x_ld, gamma, beta, param_gs, out, y_gs, y_ld, rows, total, eps);
     SVIT_LAUNCH_CHECK("layernorm_fixed_kernel");
     return SVIT_OK;
   }
   const unsigned grid = (unsigned)((total + wpb - 1) / wpb);
-#define SVIT_LN(T)                                                                                                  \
-  layernorm_kernel<T><<<grid, wpb * 32, 0, stream>>>(x, x_gs, x_ld, gamma, beta, param_gs, (T*)y, y_gs, y_ld, rows, \
-                                                     total, h, eps)
-  switch (out_dtype) {
-    case SVIT_F32: SVIT_LN(float); break;
-    case SVIT_BF16: SVIT_LN(__nv_bfloat16); break;
-    case SVIT_F16: SVIT_LN(__half); break;
-    default: SVIT_FAIL(SVIT_ERR_ARG, "layernorm: bad dtype %d", out_dtype);
-  }
-#undef SVIT_LN
+  layernorm_kernel<Out><<<grid, wpb * 32, 0, stream>>>(x, x_gs, x_ld, gamma, beta, param_gs, out, y_gs, y_ld, rows, total, h, eps);
   SVIT_LAUNCH_CHECK("layernorm_kernel");
   return SVIT_OK;
+}
+
+int layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, const float* beta, int64_t param_gs,
+              const Operand& y, int64_t y_gs, int64_t y_ld, int out_dtype, int G, int64_t rows, int h, float eps,
+              cudaStream_t stream) {
+  SVIT_CHECK_ARG(h % 4 == 0 && h <= kLnMaxVec * 128, "layernorm: h=%d must be a multiple of 4 and <= 1024", h);
+  SVIT_CHECK_ARG(x_ld % 4 == 0 && y_ld % 4 == 0 && x_gs % 4 == 0 && y_gs % 4 == 0 && param_gs % 4 == 0, "layernorm: strides must be multiples of 4");
+  if ((int64_t)G * rows == 0) return SVIT_OK;
+  int rc = SVIT_OK;
+  SVIT_WITH_OUT(y, rc = launch_layernorm(out_, x, x_gs, x_ld, gamma, beta, param_gs, y_gs, y_ld, G, rows, h, eps, stream));
+  return rc;
 }
 
 int embed_cls(float* X, int64_t x_gs, const float* wvec, int64_t vec_stride, int64_t off_cls, int64_t off_pos, int G,
@@ -334,21 +343,22 @@ int head(const float* X, int64_t x_gs, const float* wvec, int64_t vec_stride, in
 }  // namespace svit
 
 extern "C" int svit_layernorm(const float* x, int64_t x_gs, int64_t x_ld, const float* gamma, const float* beta,
-                              int64_t param_gs, void* y, int64_t y_gs, int64_t y_ld, int out_dtype, int G, int64_t rows,
-                              int h, float eps, svit_stream_t stream) {
+                              int64_t param_gs, void* y, int64_t y_gs, int64_t y_ld, int out_dtype, int out_fmt,
+                              int64_t out_alloc, int G, int64_t rows, int h, float eps, svit_stream_t stream) {
   using namespace svit;
   SVIT_CHECK_ARG(x && gamma && beta && y, "svit_layernorm: null pointer");
   SVIT_CHECK_ARG(G >= 1 && rows >= 0, "svit_layernorm: bad sizes");
+  SVIT_CHECK_ARG(out_fmt == SVIT_FMT_PLAIN || out_alloc % 16 == 0, "svit_layernorm: plane pitch must be a multiple of 16");
   if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || !aligned16(y))
     SVIT_FAIL(SVIT_ERR_ALIGN, "svit_layernorm: pointers must be 16-byte aligned");
-  return layernorm(x, x_gs, x_ld, gamma, beta, param_gs, y, y_gs, y_ld, out_dtype, G, rows, h, eps,
+  return layernorm(x, x_gs, x_ld, gamma, beta, param_gs, Operand{y, out_fmt, out_alloc}, y_gs, y_ld, out_dtype, G, rows, h, eps,
                    static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int svit_split_f16(const float* in, int64_t in_gs, void* out, int G, int64_t rows, int K,
-                              svit_stream_t stream) {
+extern "C" int svit_split_operand(const float* in, void* out, int64_t out_alloc, int out_fmt, int64_t elems,
+                                  svit_stream_t stream) {
   using namespace svit;
-  SVIT_CHECK_ARG(in && out && G >= 1 && rows >= 0 && K >= 8, "svit_split_f16: bad arguments");
-  if (!aligned16(in) || !aligned16(out)) SVIT_FAIL(SVIT_ERR_ALIGN, "svit_split_f16: pointers must be 16-byte aligned");
-  return split_f16(in, in_gs, out, G, rows, K, static_cast<cudaStream_t>(stream));
+  SVIT_CHECK_ARG(in && out && elems >= 0, "svit_split_operand: bad arguments");
+  if (!aligned16(in) || !aligned16(out)) SVIT_FAIL(SVIT_ERR_ALIGN, "svit_split_operand: pointers must be 16-byte aligned");
+  return split_operand(in, Operand{out, out_fmt, out_alloc}, elems, static_cast<cudaStream_t>(stream));
 }

@@ -14,10 +14,13 @@ struct EpiArgs {
   const float* bias;      // [N] (+ g * bias_gs) or null
   const float* rowvec;    // [rows_out, N] (+ g * rowvec_gs) or null
   const float* residual;  // fp32 [M_out, N] (+ g * residual_gs) or null; may alias out
-  void* out;              // [M_out, N] (+ g * out_gs) in out_dtype
+  void* out;              // [M_out, N] (+ g * out_gs) in out_dtype; split formats: the main plane of a packed operand array
   int64_t bias_gs, rowvec_gs, residual_gs, out_gs;
   int32_t gelu, rows_in, rows_out, row_shift, out_dtype;
   int32_t M, N;
+  int32_t out_fmt;        // svit_operand_format of `out` (split formats: out_dtype is SVIT_F16)
+  int64_t out_alloc;      // plane pitch of `out` in elements (split formats)
+  __host__ __device__ __forceinline__ Operand out_operand() const { return Operand{out, out_fmt, out_alloc}; }
 };
 
 __device__ __forceinline__ int64_t epi_out_row(const EpiArgs& e, int r) {
@@ -36,6 +39,22 @@ __device__ __forceinline__ float epi_apply(const EpiArgs& e, int g, int64_t orow
 
 __device__ __forceinline__ void epi_store(const EpiArgs& e, int g, int64_t orow, int n, float v) {
   const size_t idx = (size_t)g * e.out_gs + (size_t)orow * e.N + n;
+  if (e.out_fmt != SVIT_FMT_PLAIN) {  // element-wise (slow path): the planes of one value
+    const Operand o = e.out_operand();
+    uint32_t hi;
+    if (e.out_fmt == SVIT_FMT_X3) {
+      uint32_t lo;
+      split_x3(v, 0.f, hi, lo);
+      reinterpret_cast<uint16_t*>(o.aux1())[idx] = (uint16_t)lo;
+    } else {
+      uint16_t h8, l8;
+      split_c8(v, 0.f, hi, h8, l8);
+      reinterpret_cast<uint8_t*>(o.aux1())[idx] = (uint8_t)h8;
+      reinterpret_cast<uint8_t*>(o.aux2())[idx] = (uint8_t)l8;
+    }
+    reinterpret_cast<uint16_t*>(o.base)[idx] = (uint16_t)hi;
+    return;
+  }
   if (e.out_dtype == SVIT_F32)
     reinterpret_cast<float*>(e.out)[idx] = v;
   else if (e.out_dtype == SVIT_BF16)
@@ -63,13 +82,23 @@ inline EpiArgs make_epi(const svit_epilogue* epi, void* out, int64_t out_gs, int
   e.out_dtype = out_dtype;
   e.M = M;
   e.N = N;
+  e.out_fmt = SVIT_FMT_PLAIN;
+  e.out_alloc = 0;
   return e;
+}
+// `out` is a packed operand array (main plane at e.out) of `alloc` elements
+inline void set_out_format(EpiArgs& e, int fmt, int64_t alloc) {
+  e.out_fmt = fmt;
+  e.out_alloc = alloc;
+  if (fmt != SVIT_FMT_PLAIN) e.out_dtype = SVIT_F16;
 }
 
 // internal GEMM entry points (gemm_simt.cu / gemm_tc.cu)
 int gemm_simt(int operand_dtype, const void* A, int64_t a_gs, const void* B, int64_t b_gs, int G, int M, int N, int K,
               const EpiArgs& epi, cudaStream_t stream);
-int gemm_tc(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, int G, int M, int N, int K,
-            const EpiArgs& epi, cudaStream_t stream);
+// A / B: operand arrays in the format of `precision` (PLAIN for tf32 / bf16 / f16, X3 / C8 packed arrays for the
+// split precisions), a_off / b_off the element offset of the operand inside its array
+int gemm_tc(int precision, const Operand& A, int64_t a_off, int64_t a_gs, const Operand& B, int64_t b_off, int64_t b_gs, int G,
+            int M, int N, int K, const EpiArgs& epi, cudaStream_t stream);
 
 }  // namespace svit

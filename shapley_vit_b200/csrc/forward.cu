@@ -13,6 +13,12 @@
 //   CTX  operand  [C, B*T, h]   attention output
 //   H    operand  [C, B*T, ff]  GELU(MLP up)
 //
+// "operand" = the plan's operand format: a plain fp32 / bf16 / fp16 array, or -- in the split precisions
+// SVIT_PREC_F16X3 / F16C8 -- a packed operand array of planes (include/svit.h) that the PRODUCER of each
+// tensor writes directly (svit_aggregate_split, LayerNorm, the GEMM epilogues, attention): no separate
+// split pass, no fp32 copy of any activation.  QKV is always X3 planes there (attention runs hi / lo fp16
+// in both split precisions); Xn, CTX and H are in the GEMMs' format.
+//
 // Per layer: LN -> QKV GEMM(+bias) -> fused-softmax attention -> proj GEMM(+bias +residual, in
 // place on X) -> LN -> MLP-up GEMM(+bias +GELU) -> MLP-down GEMM(+bias +residual).  The patch
 // embedding is one GEMM whose A operand (the patchified validation images) is shared by all
@@ -35,7 +41,8 @@ struct svit_plan {
   bool full_last_layer = false;  // SVIT_FULL_LAST_LAYER=1: compute every token of the last layer (A/B and tests)
   // workspace byte offsets for (max_c, max_b)
   size_t off_x = 0, off_xn = 0, off_qkv = 0, off_ctx = 0, off_h = 0, ws_bytes = 0;
-  size_t off_sa = 0, off_sb = 0;  // SVIT_PREC_F16X3: [hi | lo] fp16 copies of the current GEMM's A and B operands
+  int fmt = 0;                    // svit_operand_format of the GEMM operands (weights, patches, Xn, CTX, H)
+  int64_t rows_max = 0;           // max_c * max_b * T: the plane pitches of the activation arrays are rows_max * width
   // optional per-kernel-class device timing (svit_plan_timing_begin / _end)
   bool timing = false;
   struct Span {
@@ -43,7 +50,6 @@ struct svit_plan {
     int cls;
     double work;  // flops (GEMM, attention) or bytes (others)
   };
-  void *split_a = nullptr, *split_b = nullptr;  // set per svit_forward_batched call (workspace + off_sa / off_sb)
   std::vector<Span> spans;
   std::vector<cudaEvent_t> pool;
   size_t pool_used = 0;
@@ -55,10 +61,11 @@ namespace {
 int operand_dtype_of(int precision) {
   switch (precision) {
     case SVIT_PREC_F32:
-    case SVIT_PREC_TF32:
-    case SVIT_PREC_F16X3: return SVIT_F32;
+    case SVIT_PREC_TF32: return SVIT_F32;
     case SVIT_PREC_BF16: return SVIT_BF16;
-    case SVIT_PREC_F16: return SVIT_F16;
+    case SVIT_PREC_F16:
+    case SVIT_PREC_F16X3:
+    case SVIT_PREC_F16C8: return SVIT_F16;  // (split precisions: the main plane)
     default: return -1;
   }
 }
@@ -92,21 +99,14 @@ struct Timed {
   }
 };
 
-int gemm_dispatch(svit_plan* p, const void* A, int64_t a_gs, const void* B, int64_t b_gs, int G, int M, int N,
-                  int K, const EpiArgs& epi, cudaStream_t stream) {
+int gemm_dispatch(svit_plan* p, const Operand& A, int64_t a_off, int64_t a_gs, const Operand& B, int64_t b_off, int64_t b_gs,
+                  int G, int M, int N, int K, const EpiArgs& epi, cudaStream_t stream) {
   Timed t(p, stream, SVIT_CLS_GEMM, 2.0 * G * M * (double)N * K);
-  if (p->precision == SVIT_PREC_F32 || p->force_simt)
-    return gemm_simt(p->operand_dtype, A, a_gs, B, b_gs, G, M, N, K, epi, stream);
-  if (p->precision == SVIT_PREC_F16X3) {
-    // fp32 operands -> [hi | lo] fp16 rows in the plan's scratch, then hi*hi + hi*lo + lo*hi on the tensor cores
-    const int ga = a_gs ? G : 1;
-    int rc;
-    if ((rc = split_f16(static_cast<const float*>(A), a_gs, p->split_a, ga, M, K, stream))) return rc;
-    if ((rc = split_f16(static_cast<const float*>(B), b_gs, p->split_b, G, N, K, stream))) return rc;
-    return gemm_tc(p->precision, p->split_a, a_gs ? (int64_t)M * 2 * K : 0, p->split_b, (int64_t)N * 2 * K, G, M, N, K, epi,
-                   stream);
+  if (p->precision == SVIT_PREC_F32 || (p->force_simt && p->fmt == SVIT_FMT_PLAIN)) {
+    const int es = dtype_size(p->operand_dtype);
+    return gemm_simt(p->operand_dtype, A.plane(0, a_off, es), a_gs, B.plane(0, b_off, es), b_gs, G, M, N, K, epi, stream);
   }
-  return gemm_tc(p->precision, A, a_gs, B, b_gs, G, M, N, K, epi, stream);
+  return gemm_tc(p->precision, A, a_off, a_gs, B, b_off, b_gs, G, M, N, K, epi, stream);
 }
 
 }  // namespace
@@ -133,6 +133,11 @@ extern "C" int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_
   }
   p->precision = precision;
   p->operand_dtype = odt;
+  p->fmt = format_of_precision(precision);
+  if (p->fmt != SVIT_FMT_PLAIN && cfg->hidden / cfg->heads != 64) {
+    delete p;
+    SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "svit_plan_create: the split precisions take head_dim 64");
+  }
   p->max_c = max_coalitions;
   p->max_b = max_images;
   p->np = (cfg->image / cfg->patch) * (cfg->image / cfg->patch);
@@ -143,7 +148,8 @@ extern "C" int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_
   const char* fl = getenv("SVIT_FULL_LAST_LAYER");
   p->full_last_layer = fl && fl[0] == '1';
   const size_t rows = (size_t)max_coalitions * max_images * p->T;
-  const size_t es = (size_t)dtype_size(odt);
+  p->rows_max = (int64_t)rows;
+  const size_t es = p->fmt == SVIT_FMT_PLAIN ? (size_t)dtype_size(odt) : 4;  // bytes per element over all planes
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -155,12 +161,6 @@ extern "C" int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_
   p->off_qkv = take(rows * 3 * cfg->hidden * es);
   p->off_ctx = take(rows * cfg->hidden * es);
   p->off_h = take(rows * cfg->ff * es);
-  if (precision == SVIT_PREC_F16X3) {
-    const size_t kmax = (size_t)std::max(std::max(cfg->hidden, cfg->ff), p->pd);
-    const size_t nk = std::max((size_t)cfg->hidden * cfg->ff, std::max((size_t)3 * cfg->hidden * cfg->hidden, (size_t)cfg->hidden * p->pd));
-    p->off_sa = take(rows * kmax * 4);  // [rows, 2K] fp16
-    p->off_sb = take((size_t)max_coalitions * nk * 4);
-  }
   p->ws_bytes = off;
   *out = p;
   return SVIT_OK;
@@ -175,19 +175,30 @@ extern "C" int svit_plan_destroy(svit_plan* plan) {
 
 extern "C" int64_t svit_plan_workspace_bytes(const svit_plan* plan) { return plan ? (int64_t)plan->ws_bytes : -1; }
 extern "C" int svit_plan_operand_dtype(const svit_plan* plan) { return plan ? plan->operand_dtype : -1; }
+extern "C" int svit_plan_operand_format(const svit_plan* plan) { return plan ? plan->fmt : -1; }
 
-extern "C" int svit_patchify(const svit_plan* plan, const float* images, void* patches, int64_t n,
-                             svit_stream_t stream) {
+extern "C" int svit_patchify(const svit_plan* plan, const float* images, void* patches, int64_t patches_alloc, int64_t row0,
+                             int64_t n, svit_stream_t stream) {
   using namespace svit;
-  SVIT_CHECK_ARG(plan && images && patches && n >= 0, "svit_patchify: bad arguments");
+  SVIT_CHECK_ARG(plan && images && patches && n >= 0 && row0 >= 0, "svit_patchify: bad arguments");
   if (!aligned16(images) || !aligned16(patches)) SVIT_FAIL(SVIT_ERR_ALIGN, "svit_patchify: pointers must be 16-byte aligned");
   const svit_vit_cfg& c = plan->lay.cfg;
-  return patchify(plan->operand_dtype, images, patches, n, c.channels, c.image, c.patch, static_cast<cudaStream_t>(stream));
+  const int64_t pd = plan->pd;
+  SVIT_CHECK_ARG(plan->fmt == SVIT_FMT_PLAIN || (patches_alloc % 16 == 0 && patches_alloc >= (row0 + n * plan->np) * pd),
+                 "svit_patchify: plane pitch %lld does not cover the rows written", (long long)patches_alloc);
+  Operand dst{patches, plan->fmt, patches_alloc};
+  int64_t off = row0 * pd;
+  if (plan->fmt == SVIT_FMT_PLAIN) {  // plain array: just a pointer
+    dst.base = dst.plane(0, off, dtype_size(plan->operand_dtype));
+    off = 0;
+  }
+  return patchify_at(plan->operand_dtype, images, dst, off, n, c.channels, c.image, c.patch, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat,
-                                    int64_t mat_stride, const void* patches, float* logits, int64_t logits_stride,
-                                    int C, int B, void* workspace, size_t workspace_bytes, svit_stream_t stream_) {
+                                    int64_t mat_stride, int64_t wmat_alloc, const void* patches, int64_t patches_alloc,
+                                    int64_t patches_row0, float* logits, int64_t logits_stride, int C, int B,
+                                    void* workspace, size_t workspace_bytes, svit_stream_t stream_) {
   using namespace svit;
   SVIT_CHECK_ARG(plan && wvec && wmat && patches && logits && workspace, "svit_forward_batched: null pointer");
   SVIT_CHECK_ARG(C >= 1 && C <= plan->max_c && B >= 1 && B <= plan->max_b,
@@ -201,23 +212,28 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
   SVIT_CHECK_ARG(logits_stride >= (int64_t)B * cfg.n_cls, "svit_forward_batched: logits_stride too small");
   if (!aligned16(wvec) || !aligned16(wmat) || !aligned16(patches) || ((uintptr_t)workspace & 255))
     SVIT_FAIL(SVIT_ERR_ALIGN, "svit_forward_batched: weights/patches must be 16-byte and workspace 256-byte aligned");
+  const int fmt = plan->fmt;
+  const bool split = fmt != SVIT_FMT_PLAIN;
+  SVIT_CHECK_ARG(!split || (wmat_alloc % 16 == 0 && patches_alloc % 16 == 0 && wmat_alloc >= (int64_t)(C - 1) * mat_stride + L.mat_size),
+                 "svit_forward_batched: bad plane pitches for the split-format weights / patches");
 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int h = cfg.hidden, ff = cfg.ff, T = plan->T, np = plan->np, pd = plan->pd;
   const int M = B * T;
   const int odt = plan->operand_dtype;
-  const size_t es = (size_t)dtype_size(odt);
   char* ws = static_cast<char*>(workspace);
   float* X = reinterpret_cast<float*>(ws + plan->off_x);
-  void* Xn = ws + plan->off_xn;
-  void* QKV = ws + plan->off_qkv;
-  void* CTX = ws + plan->off_ctx;
-  void* H = ws + plan->off_h;
-  plan->split_a = ws + plan->off_sa;
-  plan->split_b = ws + plan->off_sb;
-  const char* wm = static_cast<const char*>(wmat);
-  auto mat = [&](int kind, int layer) -> const void* { return wm + (size_t)L.find(kind, layer) * es; };
+  // activation arrays: their plane pitch is the plan's maximum row count times the width
+  const Operand Xn{ws + plan->off_xn, fmt, plan->rows_max * h};
+  const Operand QKV{ws + plan->off_qkv, split ? SVIT_FMT_X3 : SVIT_FMT_PLAIN, plan->rows_max * 3 * h};
+  const Operand CTX{ws + plan->off_ctx, fmt, plan->rows_max * h};
+  const Operand H{ws + plan->off_h, fmt, plan->rows_max * ff};
+  const Operand WM{const_cast<void*>(wmat), fmt, wmat_alloc};
+  const Operand PA{const_cast<void*>(patches), fmt, patches_alloc};
+  const int es = dtype_size(odt);
+  auto mat = [&](int kind, int layer) -> int64_t { return L.find(kind, layer); };  // element offset inside a coalition's mat row
   auto vec = [&](int kind, int layer) -> const float* { return wvec + L.find(kind, layer); };
+  auto out_op = [&](EpiArgs& ea, const Operand& o) { if (split) set_out_format(ea, o.fmt, o.alloc); };
   const int64_t xgs = (int64_t)M * h;
   int rc;
 
@@ -234,12 +250,13 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
     e.rows_out = T;
     e.row_shift = 1;
     EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, B * np, h);
-    if ((rc = gemm_dispatch(plan, patches, 0, mat(SVIT_SEG_PATCH_W, -1), mat_stride, C, B * np, h, pd, ea, stream))) return rc;
+    if ((rc = gemm_dispatch(plan, PA, patches_row0 * pd, 0, WM, mat(SVIT_SEG_PATCH_W, -1), mat_stride, C, B * np, h, pd, ea, stream)))
+      return rc;
   }
   // ---- encoder ----
   for (int l = 0; l < cfg.layers; ++l) {
     {
-      Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * M * h * (4.0 + es));
+      Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * M * h * (4.0 + (split ? 4 : es)));
       if ((rc = layernorm(X, xgs, h, vec(SVIT_SEG_LN1_G, l), vec(SVIT_SEG_LN1_B, l), vec_stride, Xn, xgs, h, odt, C, M, h,
                           cfg.ln_eps, stream)))
         return rc;
@@ -248,8 +265,9 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       svit_epilogue e{};
       e.bias = vec(SVIT_SEG_BQ, l);  // bq | bk | bv are contiguous
       e.bias_gs = vec_stride;
-      EpiArgs ea = make_epi(&e, QKV, (int64_t)M * 3 * h, odt, M, 3 * h);
-      if ((rc = gemm_dispatch(plan, Xn, xgs, mat(SVIT_SEG_WQ, l), mat_stride, C, M, 3 * h, h, ea, stream))) return rc;
+      EpiArgs ea = make_epi(&e, QKV.base, (int64_t)M * 3 * h, odt, M, 3 * h);
+      out_op(ea, QKV);
+      if ((rc = gemm_dispatch(plan, Xn, 0, xgs, WM, mat(SVIT_SEG_WQ, l), mat_stride, C, M, 3 * h, h, ea, stream))) return rc;
     }
     if (l == cfg.layers - 1 && !plan->full_last_layer) {
       // Last layer: the classifier reads only the [CLS] token (HF modeling_vit.py:641-642), so past
@@ -258,7 +276,9 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       const int64_t cgs = (int64_t)B * h;  // compact [C, B, h] buffers live at the front of CTX / Xn / H
       {
         Timed t(plan, stream, SVIT_CLS_ATTENTION, 4.0 * C * B * (double)T * h);
-        if ((rc = attention_cls(QKV, CTX, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream))) return rc;
+        if (split) rc = attention_split(QKV, CTX, (int64_t)C * B, T, cfg.heads, h / cfg.heads, true, stream);
+        else rc = attention_cls(QKV.base, CTX.base, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream);
+        if (rc) return rc;
       }
       auto cls_rows = [&](svit_epilogue& e) { e.rows_in = 1, e.rows_out = T, e.row_shift = 0; };  // row b -> X row b * T
       {
@@ -269,10 +289,10 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
         e.residual_gs = xgs;
         cls_rows(e);
         EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, B, h);
-        if ((rc = gemm_dispatch(plan, CTX, cgs, mat(SVIT_SEG_WO, l), mat_stride, C, B, h, h, ea, stream))) return rc;
+        if ((rc = gemm_dispatch(plan, CTX, 0, cgs, WM, mat(SVIT_SEG_WO, l), mat_stride, C, B, h, h, ea, stream))) return rc;
       }
       {
-        Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * B * h * (4.0 + es));
+        Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * B * h * (4.0 + (split ? 4 : es)));
         if ((rc = layernorm(X, xgs, (int64_t)T * h, vec(SVIT_SEG_LN2_G, l), vec(SVIT_SEG_LN2_B, l), vec_stride, Xn, cgs, h, odt,
                             C, B, h, cfg.ln_eps, stream)))
           return rc;
@@ -282,8 +302,9 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
         e.bias = vec(SVIT_SEG_B1, l);
         e.bias_gs = vec_stride;
         e.gelu = 1;
-        EpiArgs ea = make_epi(&e, H, (int64_t)B * ff, odt, B, ff);
-        if ((rc = gemm_dispatch(plan, Xn, cgs, mat(SVIT_SEG_W1, l), mat_stride, C, B, ff, h, ea, stream))) return rc;
+        EpiArgs ea = make_epi(&e, H.base, (int64_t)B * ff, odt, B, ff);
+        out_op(ea, H);
+        if ((rc = gemm_dispatch(plan, Xn, 0, cgs, WM, mat(SVIT_SEG_W1, l), mat_stride, C, B, ff, h, ea, stream))) return rc;
       }
       {
         svit_epilogue e{};
@@ -293,16 +314,14 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
         e.residual_gs = xgs;
         cls_rows(e);
         EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, B, h);
-        if ((rc = gemm_dispatch(plan, H, (int64_t)B * ff, mat(SVIT_SEG_W2, l), mat_stride, C, B, h, ff, ea, stream))) return rc;
+        if ((rc = gemm_dispatch(plan, H, 0, (int64_t)B * ff, WM, mat(SVIT_SEG_W2, l), mat_stride, C, B, h, ff, ea, stream))) return rc;
       }
       continue;
     }
     {
       Timed t(plan, stream, SVIT_CLS_ATTENTION, 4.0 * C * B * (double)T * T * h);
-      if (plan->precision == SVIT_PREC_F16X3 && h / cfg.heads == 64)  // split-precision tensor-core attention
-        rc = attention_split(static_cast<const float*>(QKV), static_cast<float*>(CTX), (int64_t)C * B, T, cfg.heads, stream);
-      else
-        rc = attention(QKV, CTX, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream);
+      if (split) rc = attention_split(QKV, CTX, (int64_t)C * B, T, cfg.heads, h / cfg.heads, false, stream);
+      else rc = attention(QKV.base, CTX.base, odt, (int64_t)C * B, T, cfg.heads, h / cfg.heads, stream);
       if (rc) return rc;
     }
     {
@@ -312,10 +331,10 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       e.residual = X;
       e.residual_gs = xgs;
       EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, M, h);
-      if ((rc = gemm_dispatch(plan, CTX, xgs, mat(SVIT_SEG_WO, l), mat_stride, C, M, h, h, ea, stream))) return rc;
+      if ((rc = gemm_dispatch(plan, CTX, 0, xgs, WM, mat(SVIT_SEG_WO, l), mat_stride, C, M, h, h, ea, stream))) return rc;
     }
     {
-      Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * M * h * (4.0 + es));
+      Timed t(plan, stream, SVIT_CLS_LAYERNORM, (double)C * M * h * (4.0 + (split ? 4 : es)));
       if ((rc = layernorm(X, xgs, h, vec(SVIT_SEG_LN2_G, l), vec(SVIT_SEG_LN2_B, l), vec_stride, Xn, xgs, h, odt, C, M, h,
                           cfg.ln_eps, stream)))
         return rc;
@@ -325,8 +344,9 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       e.bias = vec(SVIT_SEG_B1, l);
       e.bias_gs = vec_stride;
       e.gelu = 1;
-      EpiArgs ea = make_epi(&e, H, (int64_t)M * ff, odt, M, ff);
-      if ((rc = gemm_dispatch(plan, Xn, xgs, mat(SVIT_SEG_W1, l), mat_stride, C, M, ff, h, ea, stream))) return rc;
+      EpiArgs ea = make_epi(&e, H.base, (int64_t)M * ff, odt, M, ff);
+      out_op(ea, H);
+      if ((rc = gemm_dispatch(plan, Xn, 0, xgs, WM, mat(SVIT_SEG_W1, l), mat_stride, C, M, ff, h, ea, stream))) return rc;
     }
     {
       svit_epilogue e{};
@@ -335,7 +355,7 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       e.residual = X;
       e.residual_gs = xgs;
       EpiArgs ea = make_epi(&e, X, xgs, SVIT_F32, M, h);
-      if ((rc = gemm_dispatch(plan, H, (int64_t)M * ff, mat(SVIT_SEG_W2, l), mat_stride, C, M, h, ff, ea, stream))) return rc;
+      if ((rc = gemm_dispatch(plan, H, 0, (int64_t)M * ff, WM, mat(SVIT_SEG_W2, l), mat_stride, C, M, h, ff, ea, stream))) return rc;
     }
   }
   // ---- head ----
@@ -352,12 +372,15 @@ extern "C" int svit_gemm(int precision, const void* A, int64_t a_gs, const void*
   const int odt = operand_dtype_of(precision);
   SVIT_CHECK_ARG(odt >= 0, "svit_gemm: unknown precision %d", precision);
   SVIT_CHECK_ARG(out_dtype == SVIT_F32 || out_dtype == odt, "svit_gemm: out_dtype must be f32 or the operand dtype");
-  // (SVIT_PREC_F16X3: A and B arrive pre-split, see svit_split_f16; the output is fp32)
+  const int fmt = format_of_precision(precision);
   EpiArgs ea = make_epi(epi, out, out_gs, out_dtype, M, N);
+  const int64_t m_out = epi && epi->rows_in > 0 ? (int64_t)(M / epi->rows_in) * epi->rows_out : M;
+  if (fmt != SVIT_FMT_PLAIN && out_dtype != SVIT_F32) set_out_format(ea, fmt, (int64_t)G * m_out * N);
+  const Operand a{const_cast<void*>(A), fmt, (int64_t)(a_gs ? G : 1) * M * K}, b{const_cast<void*>(B), fmt, (int64_t)G * N * K};
   const char* env = getenv("SVIT_FORCE_SIMT_GEMM");
-  if (precision == SVIT_PREC_F32 || (precision != SVIT_PREC_F16X3 && env && env[0] == '1'))
+  if (precision == SVIT_PREC_F32 || (fmt == SVIT_FMT_PLAIN && env && env[0] == '1'))
     return gemm_simt(odt, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
-  return gemm_tc(precision, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
+  return gemm_tc(precision, a, 0, a_gs, b, 0, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int svit_plan_timing_begin(svit_plan* plan) {

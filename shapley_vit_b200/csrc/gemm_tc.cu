@@ -16,7 +16,12 @@
 //                              vector stores.  Two TMEM accumulator buffers, so the epilogue of
 //                              tile i overlaps the MMAs of tile i+1.
 // Tile order: n fastest, then m, then group, so CTAs running concurrently share A rows in L2.
-// Operand precisions: bf16 / fp16 (kind::f16, K=16 per MMA) and tf32 (kind::tf32, K=8).
+// Operand precisions: bf16 / fp16 (kind::f16, K=16 per MMA), tf32 (kind::tf32, K=8), and the two split
+// precisions on packed operand arrays (include/svit.h):
+//   F16X3  the K loop runs three passes over the fp16 planes: hi*lo, lo*hi, hi*hi (small terms first)
+//   F16C8  two e4m3 compensation passes (kind::f8f6f4, K=32 per MMA, twice the f16 rate): hi8*lo8, lo8*hi8,
+//          then the fp16 pass, whose FIRST MMA folds the compensation in with scale-input-d:
+//          D = A*B + D * 2^-15.  One accumulator, one epilogue, 2 instead of 3 f16-pass equivalents.
 //
 // Two kernels share the roles above:
 //   gemm_tc_kernel   one CTA per 128 x BN tile (cta_group::1); any N (BN = 128 | 256)
@@ -181,6 +186,38 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
         : "memory");
   }
 }
+// e4m3 x e4m3 -> fp32 (the compensation passes of SVIT_PREC_F16C8); same instruction descriptor bits as fp16
+__device__ __forceinline__ void tc_mma_f8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// D = A * B + D * 2^-SVIT_C8_SCALE_D (scale-input-d, kind::f16 only): rescales the accumulated compensation
+__device__ __forceinline__ void tc_mma_scaled_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%4, %4, %4, %4, %4, %4, %4, %4}, p, %5;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(z), "n"(SVIT_C8_SCALE_D)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_scaled(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %4, %4, %4}, p, %5;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(z), "n"(SVIT_C8_SCALE_D)
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (row) i
 __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -209,16 +246,35 @@ struct TcShape {
   int tiles_m, tiles_n, num_kb;
   int64_t total_tiles;
   int a_grouped;  // 0: A shared by all groups
-  int split_kb;   // > 0: operands are [hi | lo] halves of split_kb k-blocks each; the K loop runs hi*hi, hi*lo, lo*hi
+  int mode;       // svit_operand_format of the operands: the schedule of the K loop
+  int nk_main;    // k-blocks of one fp16 / tf32 pass (128 bytes of K each)
+  int nk_aux;     // C8: k-blocks (128 e4m3 values of K) of one compensation pass
 };
 
-// k-block of A and of B read by step kb of the K loop (identity unless the operands are split)
-__device__ __forceinline__ void split_blocks(const TcShape& sh, int kb, int& ka, int& kw) {
-  ka = kb, kw = kb;
-  if (sh.split_kb) {
-    const int nk = sh.split_kb;
-    if (kb >= 2 * nk) ka = kb - nk, kw = kb - 2 * nk;  // A lo * B hi
-    else if (kb >= nk) ka = kb - nk;                   // A hi * B lo
+// the operand planes (main, aux1, aux2) of A and of B; unused entries repeat the main plane
+struct TcMaps {
+  CUtensorMap a[3], b[3];
+};
+
+// Step kb of the K loop: planes of A and B it multiplies and the K coordinate (elements) of its 128-byte block.
+//   PLAIN  (A0, B0) x nk_main
+//   X3     (A0 hi, B1 lo) x nk, (A1 lo, B0 hi) x nk, (A0 hi, B0 hi) x nk          -- small terms first
+//   C8     (A1 hi8, B2 lo8) x nk_aux, (A2 lo8, B1 hi8) x nk_aux [kind::f8f6f4], then (A0, B0) x nk_main [kind::f16]
+template <int KIND>
+__device__ __forceinline__ void kstep(const TcShape& sh, int kb, int& ia, int& ib, int& kc) {
+  constexpr int BKE = KIND == 0 ? 64 : 32;
+  ia = 0, ib = 0, kc = kb * BKE;
+  if (KIND != 0 || sh.mode == SVIT_FMT_PLAIN) return;
+  if (sh.mode == SVIT_FMT_X3) {
+    const int nk = sh.nk_main;
+    if (kb < nk) ib = 1;
+    else if (kb < 2 * nk) ia = 1, kc = (kb - nk) * 64;
+    else kc = (kb - 2 * nk) * 64;
+  } else {
+    const int n8 = sh.nk_aux;
+    if (kb < n8) ia = 1, ib = 2, kc = kb * 128;
+    else if (kb < 2 * n8) ia = 2, ib = 1, kc = (kb - n8) * 128;
+    else kc = (kb - 2 * n8) * 64;
   }
 }
 
@@ -306,7 +362,7 @@ __device__ __forceinline__ void residual_prefetch(const EpiArgs& e, int g, int m
 //   stg      this warp's staging tile (kStagingPerWarp bytes of shared memory)
 //   res      this chunk's residual fragment (residual_prefetch), ignored unless the mode adds one
 //   bias_s   this chunk's 32 bias values in shared memory (staged per tile), ignored unless e.bias
-template <int MODE>
+template <int MODE, int OFMT>
 __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, int g, int m_slab, int n, float* v, uint8_t* stg,
                                                int lane, const float4 (&res)[8], const float* bias_s) {
   const int N = e.N, M = e.M;
@@ -335,12 +391,40 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, int g, int m_sl
   if (stage16) {
     // 16-bit tile: rows of 64 bytes, 16-byte chunk j of row r at chunk (j ^ ((r >> 1) & 3))
     uint32_t w[16];
-    if (e.out_dtype == SVIT_BF16) {
+    uint32_t x[OFMT == SVIT_FMT_PLAIN ? 1 : 16];  // X3: the lo16 pairs; C8: x[0..7] hi8, x[8..15] lo8 (4 values per word)
+    if constexpr (OFMT == SVIT_FMT_X3) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) split_x3(v[2 * i], v[2 * i + 1], w[i], x[i]);
+    } else if constexpr (OFMT == SVIT_FMT_C8) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        uint16_t h0, l0, h1, l1;
+        split_c8(v[2 * i], v[2 * i + 1], w[i], h0, l0);
+        split_c8(v[2 * i + 2], v[2 * i + 3], w[i + 1], h1, l1);
+        x[i >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        x[8 + (i >> 1)] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      }
+    } else if (e.out_dtype == SVIT_BF16) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
     } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) w[i] = pack_f16x2_sat(v[2 * i], v[2 * i + 1]);
+    }
+    if constexpr (OFMT == SVIT_FMT_X3) {  // the lo16 tile: same layout, 2 KB further on
+      uint8_t* lb = stg + 2048 + lane * 64;
+      const int sl = (lane >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(lb + ((j ^ sl) << 4)) = make_uint4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+    } else if constexpr (OFMT == SVIT_FMT_C8) {  // hi8 / lo8 tiles: rows of 32 bytes, chunk j of row r at (j ^ ((r >> 2) & 1))
+      uint8_t* hb = stg + 2048 + lane * 32;
+      const int sl = (lane >> 2) & 1;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        *reinterpret_cast<uint4*>(hb + ((j ^ sl) << 4)) = make_uint4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+        *reinterpret_cast<uint4*>(hb + 1024 + ((j ^ sl) << 4)) = make_uint4(x[8 + 4 * j], x[9 + 4 * j], x[10 + 4 * j], x[11 + 4 * j]);
+      }
     }
     uint8_t* wbase = stg + lane * 64;
     const int sw = (lane >> 1) & 3;
@@ -367,6 +451,37 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, int g, int m_sl
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (m_slab + i * 8 + (lane >> 2) < M) *reinterpret_cast<uint4*>(o + (size_t)(i * 8) * N) = q[i];
+    }
+    if constexpr (OFMT == SVIT_FMT_X3) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = i * 8 + (lane >> 2);
+        q[i] = *reinterpret_cast<const uint4*>(stg + 2048 + rr * 64 + ((ch ^ ((rr >> 1) & 3)) << 4));
+      }
+      uint16_t* lo = reinterpret_cast<uint16_t*>(e.out_operand().aux1()) + (size_t)g * e.out_gs + n + ch * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = m_slab + i * 8 + (lane >> 2);
+        if (row < M) *reinterpret_cast<uint4*>(lo + (size_t)(remap ? epi_out_row(e, row) : (int64_t)row) * N) = q[i];
+      }
+    } else if constexpr (OFMT == SVIT_FMT_C8) {  // 2 lanes cover one 32-byte row segment, 16 rows per access
+      const int c8 = lane & 1;
+      const Operand oo = e.out_operand();
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        uint4 r8[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int rr = i * 16 + (lane >> 1);
+          r8[i] = *reinterpret_cast<const uint4*>(stg + 2048 + pl * 1024 + rr * 32 + ((c8 ^ ((rr >> 2) & 1)) << 4));
+        }
+        uint8_t* pb = reinterpret_cast<uint8_t*>(pl == 0 ? oo.aux1() : oo.aux2()) + (size_t)g * e.out_gs + n + c8 * 16;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int row = m_slab + i * 16 + (lane >> 1);
+          if (row < M) *reinterpret_cast<uint4*>(pb + (size_t)(remap ? epi_out_row(e, row) : (int64_t)row) * N) = r8[i];
+        }
+      }
     }
   } else {
     // fp32 tile: rows of 128 bytes, 16-byte chunk j of row r at chunk (j ^ (r & 7))
@@ -465,13 +580,13 @@ __device__ __forceinline__ void epilogue_row_ragged(const EpiArgs& e, int g, int
 // accumulator, each further residual fragment one chunk ahead.  (With the loads issued where they
 // are used, an L2 round trip per chunk sat on the epilogue's critical path and the tensor pipe
 // idled a third of the time: profiles/r03_gemm_qkv.)
-template <int BN, int MODE, class Arrive>
+template <int BN, int MODE, int OFMT, class Arrive>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape& sh, int g, int m_slab, int n0, int half,
                                               int lane, uint32_t tmem_acc, uint8_t* stg, float* bias_s,
                                               uint64_t* tfull, uint32_t parity, Arrive arrive,
                                               const CUtensorMap* map_out = nullptr) {
   constexpr int NCH = BN / 64;  // 32-column chunks per warp (2 or 4)
-  const bool vec_ok = (sh.N & 7) == 0;
+  const bool vec_ok = (sh.N & (OFMT == SVIT_FMT_C8 ? 15 : 7)) == 0;  // 16-byte pieces of every output plane
   const int n_w = n0 + half * (BN / 2);
   const bool rows_ok = m_slab < sh.M;
   if (epi.bias && vec_ok) {
@@ -498,7 +613,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape&
     }
     if (n < sh.N && rows_ok) {
       if (vec_ok && n + 32 <= sh.N)
-        epilogue_chunk<MODE>(epi, g, m_slab, n, v, stg, lane, res, bias_s + 32 * c);
+        epilogue_chunk<MODE, OFMT>(epi, g, m_slab, n, v, stg, lane, res, bias_s + 32 * c);
       else if (m_slab + lane < sh.M)
         epilogue_row_ragged(epi, g, m_slab + lane, n, v);
     }
@@ -524,10 +639,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape&
 }
 
 // ---- the kernel --------------------------------------------------------------------------
-template <int BN, int KIND, int MODE>
+template <int BN, int KIND, int MODE, int OFMT>
 __global__ void __launch_bounds__(kThreads, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                   const TcShape sh, const EpiArgs epi, const uint32_t idesc) {
+    gemm_tc_kernel(const __grid_constant__ TcMaps maps, const TcShape sh, const EpiArgs epi, const uint32_t idesc) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB aligned, still a __shared__ pointer
@@ -541,8 +655,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -578,11 +692,10 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
-          constexpr int BKE = KIND == 0 ? 64 : 32;
-          int ka, kw;
-          split_blocks(sh, kb, ka, kw);
-          tma_load_3d(sa, &tma_a, &full_bar[s], ka * BKE, m0, sh.a_grouped ? g : 0);
-          tma_load_3d(sa + C::A_BYTES, &tma_b, &full_bar[s], kw * BKE, n0, g);
+          int ia, ib, kc;
+          kstep<KIND>(sh, kb, ia, ib, kc);
+          tma_load_3d(sa, &maps.a[ia], &full_bar[s], kc, m0, sh.a_grouped ? g : 0);
+          tma_load_3d(sa + C::A_BYTES, &maps.b[ib], &full_bar[s], kc, n0, g);
         }
         __syncwarp();
         if (++s == C::STAGES) s = 0, ph ^= 1;
@@ -592,6 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     int s = 0, acc = 0;
     uint32_t ph = 0, aph = 0;
     const uint64_t adesc0 = umma_desc(smem_u32(smem)), bdesc0 = umma_desc(smem_u32(smem) + C::A_BYTES);
+    const int naux = (KIND == 0 && sh.mode == SVIT_FMT_C8) ? 2 * sh.nk_aux : 0;  // e4m3 compensation k-blocks come first
     for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], aph ^ 1);
       tc_fence_after();
@@ -602,9 +716,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (elect_one()) {
           const uint64_t ad = umma_desc_advance(adesc0, (uint32_t)s * C::STAGE_BYTES);
           const uint64_t bd = umma_desc_advance(bdesc0, (uint32_t)s * C::STAGE_BYTES);
+          if (KIND == 0 && kb < naux) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes along K inside the 128-byte swizzle span
-            tc_mma<KIND>(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (uint32_t)(kb | k));
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f8(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (uint32_t)(kb | k));
+          } else if (KIND == 0 && naux && kb == naux) {  // first fp16 block: D = A*B + D * 2^-15
+            tc_mma_scaled(d_tmem, ad, bd, idesc);
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+              tc_mma<KIND>(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // 4 x 32 bytes along K inside the 128-byte swizzle span
+              tc_mma<KIND>(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (uint32_t)(kb | k));
+          }
           tc_commit(&empty_bar[s]);  // smem stage reusable once these MMAs have read it
           if (kb == sh.num_kb - 1) tc_commit(&tfull_bar[acc]);  // accumulator complete
         }
@@ -625,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int rem = (int)(tile % tiles_per_group);
       const int m0 = (rem / sh.tiles_n) * BM, n0 = (rem % sh.tiles_n) * BN;
       uint64_t* te = &tempty_bar[acc];
-      epilogue_tile<BN, MODE>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
+      epilogue_tile<BN, MODE, OFMT>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
                         tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), stg, bias_s, &tfull_bar[acc], aph,
                         [te] { mbar_arrive(te); });
       if ((acc ^= 1) == 0) aph ^= 1;
@@ -658,11 +783,10 @@ struct Cfg2 {
 template <int MODE> struct PairCfg { using type = Cfg2<5>; };
 template <> struct PairCfg<EPI_REDUCE> { using type = Cfg2<4, 2 * kStagingPerWarp>; };
 
-template <int KIND, int STAGES, int MODE>
+template <int KIND, int STAGES, int MODE, int OFMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-    gemm_tc2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                    const __grid_constant__ CUtensorMap tma_out, const TcShape sh, const EpiArgs epi,
-                    const uint32_t idesc) {
+    gemm_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ CUtensorMap tma_out, const TcShape sh,
+                    const EpiArgs epi, const uint32_t idesc) {
   using C = typename PairCfg<MODE>::type;
   static_assert(C::STAGES == STAGES, "stage count is a function of the epilogue mode");
   constexpr int BN = C::BN;
@@ -681,8 +805,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs)
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[0]) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);   // the leader's producer arrives once and expects both CTAs' bytes
       mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit
@@ -721,11 +845,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
-          constexpr int BKE = KIND == 0 ? 64 : 32;
-          int ka, kw;
-          split_blocks(sh, kb, ka, kw);
-          tma_load_3d_pair(sa, &tma_a, full0 + 8u * s, ka * BKE, m0, sh.a_grouped ? g : 0);
-          tma_load_3d_pair(sa + C::A_BYTES, &tma_b, full0 + 8u * s, kw * BKE, n0, g);
+          int ia, ib, kc;
+          kstep<KIND>(sh, kb, ia, ib, kc);
+          tma_load_3d_pair(sa, &maps.a[ia], full0 + 8u * s, kc, m0, sh.a_grouped ? g : 0);
+          tma_load_3d_pair(sa + C::A_BYTES, &maps.b[ib], full0 + 8u * s, kc, n0, g);
         }
         __syncwarp();
         if (++s == C::STAGES) s = 0, ph ^= 1;
@@ -736,6 +859,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       int s = 0, acc = 0;
       uint32_t ph = 0, aph = 0;
       const uint64_t adesc0 = umma_desc(smem_u32(smem)), bdesc0 = umma_desc(smem_u32(smem) + C::A_BYTES);
+      const int naux = (KIND == 0 && sh.mode == SVIT_FMT_C8) ? 2 * sh.nk_aux : 0;  // e4m3 compensation k-blocks come first
       for (int64_t tile = pair; tile < sh.total_tiles; tile += npairs) {
         mbar_wait(&tempty_bar[acc], aph ^ 1);
         tc_fence_after();
@@ -746,9 +870,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           if (elect_one()) {
             const uint64_t ad = umma_desc_advance(adesc0, (uint32_t)s * C::STAGE_BYTES);
             const uint64_t bd = umma_desc_advance(bdesc0, (uint32_t)s * C::STAGE_BYTES);
+            if (KIND == 0 && kb < naux) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              tc_mma_pair<KIND>(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (uint32_t)(kb | k));
+              for (int k = 0; k < 4; ++k)
+                tc_mma_f8_pair(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (uint32_t)(kb | k));
+            } else if (KIND == 0 && naux && kb == naux) {  // first fp16 block: D = A*B + D * 2^-15
+              tc_mma_scaled_pair(d_tmem, ad, bd, idesc);
+#pragma unroll
+              for (int k = 1; k < 4; ++k)
+                tc_mma_pair<KIND>(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, 1u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                tc_mma_pair<KIND>(d_tmem, umma_desc_advance(ad, k * 32), umma_desc_advance(bd, k * 32), idesc, (uint32_t)(kb | k));
+            }
             tc_commit_pair(&empty_bar[s]);  // frees stage s in both CTAs
             if (kb == sh.num_kb - 1) tc_commit_pair(&tfull_bar[acc]);  // both CTAs' halves of the accumulator are complete
           }
@@ -771,7 +906,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int rem = (int)(tile % tiles_per_group);
       const int m0 = (rem / sh.tiles_n) * (2 * BM) + (int)rank * BM, n0 = (rem % sh.tiles_n) * BN;
       const uint32_t te = tempty0 + 8u * acc;
-      epilogue_tile<BN, MODE>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
+      epilogue_tile<BN, MODE, OFMT>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
                         tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), stg, bias_s, &tfull_bar[acc], aph,
                         [te] { mbar_arrive_cluster(te); }, &tma_out);
       if ((acc ^= 1) == 0) aph ^= 1;
@@ -791,7 +926,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 }
 
 // ---- host side ----------------------------------------------------------------------------
-// 3-D map over a [groups, rows, K] K-contiguous operand; box = 128 bytes of K x box_rows rows.
+// 3-D map over a [groups, rows, K] K-contiguous operand plane; box = 128 bytes of K x box_rows rows.
 int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_t K, int64_t groups, int64_t gs,
              int box_rows) {
   const int es = dtype_size(dtype);
@@ -799,27 +934,41 @@ int make_map(CUtensorMap* map, int dtype, const void* base, int64_t rows, int64_
                        (uint64_t)(groups > 1 ? gs : rows * K) * es, (uint32_t)(128 / es), (uint32_t)box_rows);
 }
 
-template <int BN, int KIND>
-int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcShape sh, const EpiArgs& epi, uint32_t idesc,
-              cudaStream_t stream) {
+// the maps of every plane of one operand (unused entries repeat the main plane)
+int make_plane_maps(CUtensorMap (&maps)[3], int dtype, const Operand& op, int64_t off, int64_t rows, int64_t K, int64_t groups,
+                    int64_t gs, int box_rows) {
+  int rc;
+  const int es = dtype_size(dtype);
+  if ((rc = make_map(&maps[0], dtype, op.plane(0, off, es), rows, K, groups, gs, box_rows))) return rc;
+  maps[1] = maps[0], maps[2] = maps[0];
+  if (op.fmt == SVIT_FMT_X3) {
+    if ((rc = make_map(&maps[1], SVIT_F16, op.plane(1, off), rows, K, groups, gs, box_rows))) return rc;
+  } else if (op.fmt == SVIT_FMT_C8) {
+    if ((rc = make_map(&maps[1], SVIT_U8, op.plane(1, off), rows, K, groups, gs, box_rows))) return rc;
+    if ((rc = make_map(&maps[2], SVIT_U8, op.plane(2, off), rows, K, groups, gs, box_rows))) return rc;
+  }
+  return SVIT_OK;
+}
+
+template <int BN, int KIND, int OFMT>
+int launch_tc(const TcMaps& maps, TcShape sh, const EpiArgs& epi, uint32_t idesc, cudaStream_t stream) {
   using C = Cfg<BN>;
   sh.tiles_m = (sh.M + BM - 1) / BM;
   sh.tiles_n = (sh.N + BN - 1) / BN;
   sh.total_tiles = (int64_t)sh.G * sh.tiles_m * sh.tiles_n;
-  auto kern = gemm_tc_kernel<BN, KIND, EPI_GENERIC>;
+  auto kern = gemm_tc_kernel<BN, KIND, EPI_GENERIC, OFMT>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   const int64_t grid = std::min<int64_t>(sh.total_tiles, sm_count());
-  kern<<<(unsigned)grid, kThreads, C::SMEM, stream>>>(ma, mb, sh, epi, idesc);
+  kern<<<(unsigned)grid, kThreads, C::SMEM, stream>>>(maps, sh, epi, idesc);
   SVIT_LAUNCH_CHECK("gemm_tc_kernel");
   return SVIT_OK;
 }
 
-template <int KIND, int MODE>
-int launch_tc2s(const CUtensorMap& ma, const CUtensorMap& mb, TcShape sh, const EpiArgs& epi, uint32_t idesc,
-                cudaStream_t stream) {
+template <int KIND, int MODE, int OFMT>
+int launch_tc2s(const TcMaps& maps, TcShape sh, const EpiArgs& epi, uint32_t idesc, cudaStream_t stream) {
   using C = typename PairCfg<MODE>::type;
   constexpr int STAGES = C::STAGES;
-  CUtensorMap mo = ma;  // only the reduce mode reads it
+  CUtensorMap mo = maps.a[0];  // only the reduce mode reads it
   if (MODE == EPI_REDUCE) {
     int rc = encode_map_3d(&mo, SVIT_F32, epi.out, (uint64_t)sh.N, (uint64_t)sh.M, (uint64_t)sh.G, (uint64_t)sh.N * 4,
                            (uint64_t)(sh.G > 1 ? epi.out_gs : (int64_t)sh.M * sh.N) * 4, 32, 32);
@@ -828,73 +977,93 @@ int launch_tc2s(const CUtensorMap& ma, const CUtensorMap& mb, TcShape sh, const 
   sh.tiles_m = (sh.M + 2 * BM - 1) / (2 * BM);
   sh.tiles_n = sh.N / C::BN;
   sh.total_tiles = (int64_t)sh.G * sh.tiles_m * sh.tiles_n;
-  auto kern = gemm_tc2_kernel<KIND, STAGES, MODE>;
+  auto kern = gemm_tc2_kernel<KIND, STAGES, MODE, OFMT>;
   SVIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   const int64_t npairs = std::min<int64_t>(sh.total_tiles, sm_count() / 2);
-  kern<<<(unsigned)(2 * npairs), kThreads, C::SMEM, stream>>>(ma, mb, mo, sh, epi, idesc);
+  kern<<<(unsigned)(2 * npairs), kThreads, C::SMEM, stream>>>(maps, mo, sh, epi, idesc);
   SVIT_LAUNCH_CHECK("gemm_tc2_kernel");
   return SVIT_OK;
 }
 
+// the output format is a compile-time parameter of the epilogue (only the 16-bit store paths differ)
+template <int KIND, int MODE>
+int launch_tc2f(const TcMaps& maps, const TcShape& sh, const EpiArgs& epi, uint32_t idesc, cudaStream_t stream) {
+  if (KIND == 0 && epi.out_fmt == SVIT_FMT_X3) return launch_tc2s<KIND, MODE, KIND == 0 ? SVIT_FMT_X3 : 0>(maps, sh, epi, idesc, stream);
+  if (KIND == 0 && epi.out_fmt == SVIT_FMT_C8) return launch_tc2s<KIND, MODE, KIND == 0 ? SVIT_FMT_C8 : 0>(maps, sh, epi, idesc, stream);
+  return launch_tc2s<KIND, MODE, SVIT_FMT_PLAIN>(maps, sh, epi, idesc, stream);
+}
+
 template <int KIND>
-int launch_tc2(const CUtensorMap& ma, const CUtensorMap& mb, const TcShape& sh, const EpiArgs& epi, uint32_t idesc,
-               cudaStream_t stream) {
+int launch_tc2(const TcMaps& maps, const TcShape& sh, const EpiArgs& epi, uint32_t idesc, cudaStream_t stream) {
   static const bool no_reduce = [] { const char* e = getenv("SVIT_GEMM_NO_REDUCE"); return e && e[0] == '1'; }();
   const bool remap = epi.rows_in > 0;
-  if (!epi.rowvec && !epi.residual && !remap) return launch_tc2s<KIND, EPI_DIRECT>(ma, mb, sh, epi, idesc, stream);
+  if (!epi.rowvec && !epi.residual && !remap) return launch_tc2f<KIND, EPI_DIRECT>(maps, sh, epi, idesc, stream);
   if (!epi.rowvec && epi.residual && !remap && !epi.gelu && epi.out_dtype == SVIT_F32) {
     // in place (out IS the residual): the add can be done by the L2 (TMA reduce-add)
     if (!no_reduce && epi.residual == epi.out && (sh.G == 1 || epi.residual_gs == epi.out_gs))
-      return launch_tc2s<KIND, EPI_REDUCE>(ma, mb, sh, epi, idesc, stream);
-    return launch_tc2s<KIND, EPI_RESIDUAL>(ma, mb, sh, epi, idesc, stream);
+      return launch_tc2s<KIND, EPI_REDUCE, SVIT_FMT_PLAIN>(maps, sh, epi, idesc, stream);
+    return launch_tc2s<KIND, EPI_RESIDUAL, SVIT_FMT_PLAIN>(maps, sh, epi, idesc, stream);
   }
-  return launch_tc2s<KIND, EPI_GENERIC>(ma, mb, sh, epi, idesc, stream);
+  return launch_tc2f<KIND, EPI_GENERIC>(maps, sh, epi, idesc, stream);
+}
+
+template <int BN, int KIND>
+int launch_tc1(const TcMaps& maps, const TcShape& sh, const EpiArgs& epi, uint32_t idesc, cudaStream_t stream) {
+  if (KIND == 0 && epi.out_fmt == SVIT_FMT_X3) return launch_tc<BN, KIND, KIND == 0 ? SVIT_FMT_X3 : 0>(maps, sh, epi, idesc, stream);
+  if (KIND == 0 && epi.out_fmt == SVIT_FMT_C8) return launch_tc<BN, KIND, KIND == 0 ? SVIT_FMT_C8 : 0>(maps, sh, epi, idesc, stream);
+  return launch_tc<BN, KIND, SVIT_FMT_PLAIN>(maps, sh, epi, idesc, stream);
 }
 
 }  // namespace
 
-int gemm_tc(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, int G, int M, int N, int K,
-            const EpiArgs& epi, cudaStream_t stream) {
-  const bool split = precision == SVIT_PREC_F16X3;  // operands pre-split into [hi | lo] fp16 rows of 2K
+int gemm_tc(int precision, const Operand& A, int64_t a_off, int64_t a_gs, const Operand& B, int64_t b_off, int64_t b_gs, int G,
+            int M, int N, int K, const EpiArgs& epi, cudaStream_t stream) {
+  const int mode = format_of_precision(precision);  // operand format = schedule of the K loop
   const int dtype = precision == SVIT_PREC_TF32 ? SVIT_F32 : precision == SVIT_PREC_BF16 ? SVIT_BF16 : SVIT_F16;
-  SVIT_CHECK_ARG(precision == SVIT_PREC_TF32 || precision == SVIT_PREC_BF16 || precision == SVIT_PREC_F16 || split,
+  SVIT_CHECK_ARG(precision == SVIT_PREC_TF32 || precision == SVIT_PREC_BF16 || precision == SVIT_PREC_F16 || mode != SVIT_FMT_PLAIN,
                  "gemm_tc: precision %d has no tensor-core path", precision);
-  SVIT_CHECK_ARG(!split || K % 64 == 0, "gemm_tc: f16x3 needs K %% 64 == 0 (K=%d)", K);
-  const int Kphys = split ? 2 * K : K;  // row length of the operands in memory
+  SVIT_CHECK_ARG(A.fmt == mode && B.fmt == mode, "gemm_tc: operand formats (%d, %d) do not match precision %d", A.fmt, B.fmt,
+                 precision);
+  SVIT_CHECK_ARG(epi.out_fmt == SVIT_FMT_PLAIN || (epi.out_dtype == SVIT_F16 && !epi.rowvec && !epi.residual),
+                 "gemm_tc: a split-format output takes neither rowvec nor residual");
   const int es = dtype_size(dtype);
-  if (!aligned16(A) || !aligned16(B) || ((int64_t)K * es) % 16 || (a_gs * es) % 16 || (b_gs * es) % 16)
-    SVIT_FAIL(SVIT_ERR_ALIGN, "gemm_tc: operands must be 16-byte aligned with K*elt and group strides multiples of 16 bytes");
+  const int kal = mode == SVIT_FMT_C8 ? 16 : 16 / es;  // every plane's rows and group strides must be 16-byte multiples
+  if (!aligned16(A.base) || !aligned16(B.base) || K % kal || a_off % 16 || b_off % 16 || a_gs % kal || b_gs % kal ||
+      (mode != SVIT_FMT_PLAIN && (A.alloc % 16 || B.alloc % 16)))
+    SVIT_FAIL(SVIT_ERR_ALIGN, "gemm_tc: operands must be 16-byte aligned with K, offsets and group strides multiples of 16 bytes in every plane");
   if (N % 8 == 0) {  // the vectorised epilogue moves 16-byte pieces of bias / rowvec / residual / out
     const int oes = dtype_size(epi.out_dtype);
     if ((epi.bias && (!aligned16(epi.bias) || epi.bias_gs % 4)) || (epi.rowvec && (!aligned16(epi.rowvec) || epi.rowvec_gs % 4)) ||
-        (epi.residual && (!aligned16(epi.residual) || epi.residual_gs % 4)) || !aligned16(epi.out) || (epi.out_gs * oes) % 16)
+        (epi.residual && (!aligned16(epi.residual) || epi.residual_gs % 4)) || !aligned16(epi.out) || (epi.out_gs * oes) % 16 ||
+        (epi.out_fmt != SVIT_FMT_PLAIN && (epi.out_alloc % 16 || epi.out_gs % 16)))
       SVIT_FAIL(SVIT_ERR_ALIGN, "gemm_tc: bias/rowvec/residual/out must be 16-byte aligned with 16-byte group strides");
   }
   const int BN = (N % 256 == 0) ? 256 : 128;
   static const bool no_pair = [] { const char* e = getenv("SVIT_GEMM_NO_PAIR"); return e && e[0] == '1'; }();
   const bool pair = BN == 256 && M >= 2 * BM && !no_pair;  // CTA-pair kernel: each CTA stages half of the B tile
-  CUtensorMap ma, mb;
+  TcMaps maps;
   int rc;
-  if ((rc = make_map(&ma, dtype, A, M, Kphys, a_gs ? G : 1, a_gs, BM))) return rc;
-  if ((rc = make_map(&mb, dtype, B, N, Kphys, b_gs ? G : 1, b_gs, pair ? BN / 2 : BN))) return rc;
+  if ((rc = make_plane_maps(maps.a, dtype, A, a_off, M, K, a_gs ? G : 1, a_gs, BM))) return rc;
+  if ((rc = make_plane_maps(maps.b, dtype, B, b_off, N, K, b_gs ? G : 1, b_gs, pair ? BN / 2 : BN))) return rc;
   TcShape sh{};
   sh.G = G, sh.M = M, sh.N = N, sh.K = K;
   const int bk = 128 / es;
-  sh.num_kb = (K + bk - 1) / bk;
-  sh.split_kb = split ? sh.num_kb : 0;
-  if (split) sh.num_kb *= 3;
+  sh.mode = mode;
+  sh.nk_main = (K + bk - 1) / bk;
+  sh.nk_aux = mode == SVIT_FMT_C8 ? (K + 127) / 128 : 0;
+  sh.num_kb = mode == SVIT_FMT_X3 ? 3 * sh.nk_main : sh.nk_main + 2 * sh.nk_aux;
   sh.a_grouped = a_gs ? 1 : 0;
   SVIT_CHECK_ARG(b_gs != 0 || G == 1, "gemm_tc: B must be grouped when G > 1");
-  // instruction descriptor: D fp32, A/B format, both K-major, N, M
+  // instruction descriptor: D fp32, A/B format, both K-major, N, M (format 0 is fp16 for kind::f16 and e4m3 for
+  // kind::f8f6f4: the compensation passes of F16C8 use the same descriptor)
   const uint32_t fmt = precision == SVIT_PREC_TF32 ? 2u : precision == SVIT_PREC_BF16 ? 1u : 0u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                          ((uint32_t)((pair ? 2 * BM : BM) >> 4) << 24);
   if (pair)
-    return precision == SVIT_PREC_TF32 ? launch_tc2<1>(ma, mb, sh, epi, idesc, stream)
-                                       : launch_tc2<0>(ma, mb, sh, epi, idesc, stream);
+    return precision == SVIT_PREC_TF32 ? launch_tc2<1>(maps, sh, epi, idesc, stream) : launch_tc2<0>(maps, sh, epi, idesc, stream);
   if (precision == SVIT_PREC_TF32)
-    return BN == 256 ? launch_tc<256, 1>(ma, mb, sh, epi, idesc, stream) : launch_tc<128, 1>(ma, mb, sh, epi, idesc, stream);
-  return BN == 256 ? launch_tc<256, 0>(ma, mb, sh, epi, idesc, stream) : launch_tc<128, 0>(ma, mb, sh, epi, idesc, stream);
+    return BN == 256 ? launch_tc1<256, 1>(maps, sh, epi, idesc, stream) : launch_tc1<128, 1>(maps, sh, epi, idesc, stream);
+  return BN == 256 ? launch_tc1<256, 0>(maps, sh, epi, idesc, stream) : launch_tc1<128, 0>(maps, sh, epi, idesc, stream);
 }
 
 }  // namespace svit

@@ -39,8 +39,8 @@ class ValidationSet:
         with torch.cuda.device(self.device):
             helper = ops.Plan(cfg, precision, 1, 1, self.device)
             self.operand_dtype = helper.operand_dtype
-            self.patches = torch.empty((self.n * cfg.n_patches, cfg.patch_dim), dtype=self.operand_dtype,
-                                       device=self.device)
+            # the patch matrix in the plan's operand format (split precisions: planes, written by patchify itself)
+            self.patches = helper.operand_array((self.n * cfg.n_patches, cfg.patch_dim))
             self.upload(images, labels, helper)
             helper.close()
 
@@ -54,7 +54,7 @@ class ValidationSet:
             step = 1024
             for s in range(0, self.n, step):
                 img = images[s:s + step].to(self.device, dtype=torch.float32, non_blocking=True)
-                plan.patchify(img, out=self.patches[s * cfg.n_patches:(s + img.shape[0]) * cfg.n_patches])
+                plan.patchify(img, out=self.patches, row0=s * cfg.n_patches)
             self.labels = labels.to(self.device, dtype=torch.int64, non_blocking=True).contiguous()
             if own:
                 torch.cuda.current_stream().synchronize()
@@ -78,7 +78,7 @@ class ValidationSet:
 
 class CoalitionEngine:
     def __init__(self, cfg: VitConfig, w0, deltas, images, labels: Optional[torch.Tensor] = None,
-                 precision: str = "f16", coalition_batch: int = 8, image_chunk: int = 128,
+                 precision: str = _lib.DEFAULT_PRECISION, coalition_batch: int = 8, image_chunk: int = 128,
                  device: str | torch.device = "cuda:0", keep_logits: bool = False):
         """``images`` is either a host tensor [n, C, H, W] (with ``labels``) or a ValidationSet."""
         if not torch.cuda.is_available():
@@ -126,7 +126,7 @@ class CoalitionEngine:
                 raise ValueError("ValidationSet was built for another precision/device")
             cb = self.coalition_batch
             self.wvec = torch.empty((cb, self.lay.vec_size), dtype=torch.float32, device=self.device)
-            self.wmat = torch.empty((cb, self.lay.mat_size), dtype=self.plan.operand_dtype, device=self.device)
+            self.wmat = self.plan.operand_array((cb, self.lay.mat_size))   # aggregated weight matrices, operand format
             self.logits = torch.empty((cb, self.n_val, cfg.n_cls), dtype=torch.float32, device=self.device)
             torch.cuda.synchronize(self.device)
 
@@ -149,7 +149,7 @@ class CoalitionEngine:
         w0v = self.w0[:V] if self.w0 is not None else None
         w0m = self.w0[V:] if self.w0 is not None else None
         ops.aggregate(self.deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
-        ops.aggregate(self.deltas[:, V:], w0m, ratios, out=self.wmat[:Cn], P=Mz)
+        ops.aggregate(self.deltas[:, V:], w0m, ratios, out=self.wmat, P=Mz)
 
     def _run_batch(self, ratio_rows: Sequence[Sequence[float]],
                    image_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -172,8 +172,7 @@ class CoalitionEngine:
         lo, hi = image_range if image_range is not None else (0, self.n_val)
         for s in range(lo, hi, self.image_chunk):
             b = min(self.image_chunk, hi - s)
-            self.plan.forward(self.wvec[:Cn], self.wmat[:Cn], self.patches[s * npch:(s + b) * npch], b, logits,
-                              image_offset=s)
+            self.plan.forward(self.wvec[:Cn], self.wmat, self.patches, s * npch, b, logits, image_offset=s)
         self.kernel_launches += 2 + ((hi - lo + self.image_chunk - 1) // self.image_chunk) * (3 + 7 * cfg.layers) + 1
         if (lo, hi) == (0, self.n_val):
             correct, loss = ops.score(logits, self.labels)
@@ -230,13 +229,12 @@ class CoalitionEngine:
                 ops.aggregate_onto(D, part, ratios, part)                       # fp32, in place, two-rounding exact
             else:                                                                # last round: straight into the plan buffers
                 ops.aggregate_onto(D[:, :V], part[:, :V], ratios, self.wvec[:Cn], P=V)
-                ops.aggregate_onto(D[:, V:], part[:, V:], ratios, self.wmat[:Cn], P=Mz)
+                ops.aggregate_onto(D[:, V:], part[:, V:], ratios, self.wmat, P=Mz)
         logits = self.logits[:Cn]
         npch = cfg.n_patches
         for s in range(0, self.n_val, self.image_chunk):
             b = min(self.image_chunk, self.n_val - s)
-            self.plan.forward(self.wvec[:Cn], self.wmat[:Cn], self.patches[s * npch:(s + b) * npch], b, logits,
-                              image_offset=s)
+            self.plan.forward(self.wvec[:Cn], self.wmat, self.patches, s * npch, b, logits, image_offset=s)
         correct, loss = ops.score(logits, self.labels)
         if self.keep_logits:
             self.last_logits = logits.clone()
@@ -296,13 +294,12 @@ class CoalitionEngine:
             one = torch.ones((1, 1), dtype=torch.float32)
             V = self.lay.vec_size
             ops.aggregate(row[:, :V], None, one, out=self.wvec[:1], P=V)
-            ops.aggregate(row[:, V:], None, one, out=self.wmat[:1], P=self.lay.mat_size)
+            ops.aggregate(row[:, V:], None, one, out=self.wmat, P=self.lay.mat_size)
             logits = self.logits[:1]
             npch = self.cfg.n_patches
             for s in range(0, self.n_val, self.image_chunk):
                 b = min(self.image_chunk, self.n_val - s)
-                self.plan.forward(self.wvec[:1], self.wmat[:1], self.patches[s * npch:(s + b) * npch], b, logits,
-                                  image_offset=s)
+                self.plan.forward(self.wvec[:1], self.wmat, self.patches, s * npch, b, logits, image_offset=s)
             correct, loss = ops.score(logits, self.labels)
             if self.keep_logits:
                 self.last_logits = logits.clone()

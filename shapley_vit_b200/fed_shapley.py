@@ -65,7 +65,7 @@ def compute_utilities_lazy(args, previous_utility, client_model_all_rounds, clie
     if evaluator is None:
         if engine is None:
             a = args if isinstance(args, dict) else getattr(args, "__dict__", {})
-            precision = _lib.PRECISIONS[a.get("precision", "f16")]
+            precision = _lib.PRECISIONS[a.get("precision", _lib.DEFAULT_PRECISION)]
             device = a.get("device", dist.default_device())
             cfg = config_of(init_global_model, a.get("heads"))
             loader = fake_server.valid_loader

@@ -100,7 +100,7 @@ def evaluation(args, net, eval_loader):
     ``ValueError('loss is nan')`` exactly where the reference does.  ``args`` may carry the
     additive keys 'precision', 'device', 'image_chunk', 'heads'."""
     args = args if isinstance(args, dict) else {}
-    precision = _lib.PRECISIONS[args.get("precision", "f16")]
+    precision = _lib.PRECISIONS[args.get("precision", _lib.DEFAULT_PRECISION)]
     device = args.get("device", "cuda:0")
     sd = _clean_keys(_state_dict_of(net))
     if any(".lora_A." in k for k in sd):   # PEFT-LoRA model (reference start.py:274-283): fold the factors in

@@ -57,7 +57,7 @@ class Game:
     def engine(self) -> CoalitionEngine:
         if self._engine is None:
             a = self.server_args
-            precision = _lib.PRECISIONS[a.get("precision", "f16")]
+            precision = _lib.PRECISIONS[a.get("precision", _lib.DEFAULT_PRECISION)]
             device = a.get("device", dist.default_device())
             w0 = _clean_keys(_state_dict_of(self.init_server_model))
             is_lora = lora.is_lora_state_dict(w0)          # PEFT-wrapped model (reference start.py:274-283)

@@ -156,7 +156,7 @@ class LoraCoalitionEngine(CoalitionEngine):
         if self.base_frozen:
             qv.copy_(self.qv_base)                                   # W_0 blocks, shared by every coalition
         else:
-            ops.aggregate(self.deltas[:, V:], self.w0[V:], ratios, out=self.wmat[:Cn], P=Mz)
+            ops.aggregate(self.deltas[:, V:], self.w0[V:], ratios, out=self.wmat, P=Mz)
             for i, o in enumerate(self.qv_off):                       # the wrapped projections again, in fp32
                 ops.aggregate(self.deltas[:, V + o:V + o + hh], self.w0[V + o:V + o + hh], ratios, out=qv[:, i], P=hh)
         # A_S and B_S, averaged separately (K1 on the packed LoRA rows), then W + (alpha/r) B_S A_S per projection
@@ -166,7 +166,7 @@ class LoraCoalitionEngine(CoalitionEngine):
         ops.gemm(_lib.PREC_F32, f[:, 1], f[:, 0], residual=w, out=w, out_dtype=torch.float32)
         eye = self._eye[:Cn, :Cn]
         for i, o in enumerate(self.qv_off):                            # fp32 blocks -> operand dtype, in place in wmat
-            ops.aggregate(qv[:, i], None, eye, out=self.wmat[:Cn, o:o + hh], P=hh)
+            ops.aggregate(qv[:, i], None, eye, out=self.wmat, P=hh, col0=o)
         self.kernel_launches += 2 + self.n_proj + (0 if self.base_frozen else 1 + self.n_proj)
 
     def evaluate_state_dict(self, sd) -> Tuple[int, float]:
@@ -174,7 +174,7 @@ class LoraCoalitionEngine(CoalitionEngine):
         out = super().evaluate_state_dict(merged_state_dict(sd, self.scaling * self.r) if is_lora_state_dict(sd) else sd)
         if self.base_frozen:   # the call went through wmat[0]: restore the W_0 rows the frozen-base path relies on
             V = self.lay.vec_size
-            ops.aggregate(self.w0[V:].unsqueeze(0), None, torch.ones((1, 1)), out=self.wmat[:1], P=self.lay.mat_size)
+            ops.aggregate(self.w0[V:].unsqueeze(0), None, torch.ones((1, 1)), out=self.wmat, P=self.lay.mat_size)
         return out
 
     def merged_rows(self, ratio_rows) -> torch.Tensor:

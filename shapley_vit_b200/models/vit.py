@@ -15,11 +15,12 @@ from typing import Dict, Optional
 import torch
 from torch import nn
 
+from .._lib import DEFAULT_PRECISION
 from ..layout import VitConfig, pack_state_dict, plan_layout, state_dict_spec, vit_preset
 
 
 class ViTForImageClassification(nn.Module):
-    def __init__(self, cfg: VitConfig, precision: str = "f16"):
+    def __init__(self, cfg: VitConfig, precision: str = DEFAULT_PRECISION):
         super().__init__()
         self.cfg = cfg
         self.precision = precision
@@ -89,10 +90,10 @@ class ViTForImageClassification(nn.Module):
         one = torch.ones((1, 1), dtype=torch.float32)
         V = lay.vec_size
         wvec = ops.aggregate(row[:, :V], None, one, out_dtype=torch.float32, P=V)
-        wmat = ops.aggregate(row[:, V:], None, one, out_dtype=plan.operand_dtype, P=lay.mat_size)
+        wmat = ops.aggregate(row[:, V:], None, one, out=plan.operand_array((1, lay.mat_size)), P=lay.mat_size)
         patches = plan.patchify(pixel_values.to(torch.float32))
         logits = torch.empty((1, B, self.cfg.n_cls), dtype=torch.float32, device=dev)
-        plan.forward(wvec, wmat, patches, B, logits)
+        plan.forward(wvec, wmat, patches, 0, B, logits)
         return SimpleNamespace(logits=logits[0])
 
 
@@ -122,7 +123,7 @@ class LoraViTForImageClassification(ViTForImageClassification):
     author's client checkpoints load unchanged.  PEFT's init: A Kaiming-uniform, B zero.  ``forward`` scores the
     merged model W + (alpha / r) B A."""
 
-    def __init__(self, cfg: VitConfig, r: int = 16, lora_alpha: float = 8.0, precision: str = "f16"):
+    def __init__(self, cfg: VitConfig, r: int = 16, lora_alpha: float = 8.0, precision: str = DEFAULT_PRECISION):
         nn.Module.__init__(self)
         self.cfg, self.precision, self.r, self.lora_alpha = cfg, precision, r, lora_alpha
         self._names = []

@@ -74,7 +74,7 @@ _NEW_FLAGS = [
     (("--vit-size", "--vit_size"), dict(type=str, default="base", help="tiny | small | base | large")),
     (("--image-size", "--image_size"), dict(type=int, default=224, help="ViT input resolution")),
     (("--num-classes", "--num_classes"), dict(type=int, default=4, help="classifier width (reference: 4)")),
-    (("--dtype",), dict(type=str, default="f16", help="GEMM operand precision: f16 | bf16 | tf32 | f16x3 | f32")),
+    (("--dtype",), dict(type=str, default="f16c8", help="GEMM arithmetic: f16c8 (default: fp16 + fp8-compensated, meets the 99.9 % top-1 parity gate) | f16x3 | f32 (parity modes) | f16 | bf16 | tf32 (throughput modes, outside the gate)")),
     (("--lora-rank", "--lora_rank"), dict(type=int, default=0,
                                           help="> 0: PEFT-LoRA wrapped ViT (query / value, classifier saved) as in the "
                                                "reference's start.py:274-276 (there: 16); 0: plain ViT")),

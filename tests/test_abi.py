@@ -65,22 +65,25 @@ def test_product_has_no_cpu_path():
         ops.aggregate(torch.zeros(1, 8), None, torch.ones(1, 1))
 
 
-def test_f16x3_plan_has_fp32_operands_and_split_scratch():
-    """The split-precision mode stores fp32 operands (weights, patches) and adds the [hi | lo] scratch to the workspace."""
+def test_split_precision_plans_use_packed_fp16_planes():
+    """The split precisions keep every GEMM operand as planes of a packed operand array (4 bytes / element, main plane
+    fp16): the same workspace as an fp32-storage mode, no split scratch."""
     from shapley_vit_b200.layout import VitConfig
 
     lib = _lib.load()
     cfg = _lib.cfg_struct(VitConfig(192, 2, 3, 768, 32, 10))
     sizes = {}
-    for name in ("f16", "tf32", "f16x3"):
+    for name in ("f16", "tf32", "f16x3", "f16c8"):
         h = C.c_void_p()
         assert lib.svit_plan_create(C.byref(cfg), _lib.PRECISIONS[name], 2, 4, C.byref(h)) == 0
-        sizes[name] = (lib.svit_plan_operand_dtype(h), lib.svit_plan_workspace_bytes(h))
+        sizes[name] = (lib.svit_plan_operand_dtype(h), lib.svit_plan_operand_format(h), lib.svit_plan_workspace_bytes(h))
         assert lib.svit_plan_destroy(h) == 0
-    assert sizes["f16x3"][0] == _lib.F32 == sizes["tf32"][0] and sizes["f16"][0] == _lib.F16
-    assert sizes["f16x3"][1] > sizes["tf32"][1] > sizes["f16"][1]
+    assert sizes["f16x3"][:2] == (_lib.F16, _lib.FMT_X3) and sizes["f16c8"][:2] == (_lib.F16, _lib.FMT_C8)
+    assert sizes["tf32"][:2] == (_lib.F32, _lib.FMT_PLAIN) and sizes["f16"][:2] == (_lib.F16, _lib.FMT_PLAIN)
+    assert sizes["f16x3"][2] == sizes["f16c8"][2] == sizes["tf32"][2] > sizes["f16"][2]
     h = C.c_void_p()
     assert lib.svit_plan_create(C.byref(cfg), 7, 2, 4, C.byref(h)) == -1          # unknown precision
+    assert _lib.DEFAULT_PRECISION in ("f16c8", "f16x3", "f32")                   # the default must be a parity mode
 
 
 def test_lib_override_must_exist(monkeypatch):

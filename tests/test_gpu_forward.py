@@ -3,13 +3,16 @@ batched forward logits, per-coalition utilities, top-1 agreement and Shapley vec
 
 Tolerances are the north-star's: aggregated weights 1e-6 relative (here: bit-exact in fp32),
 >= 99.9 % top-1 agreement per coalition, utility within one sample's accuracy, Shapley within
-1e-3 absolute.  The fp32 mode (SVIT_PREC_F32) is held to all of them.  The tensor-core modes round
-GEMM operands to 11 (fp16, tf32) or 8 (bf16) significant bits; on these RANDOM-INIT weights the
-1st-percentile top-1 margin is ~0.006, so they are held to the Shapley and
-loss tolerances and to the agreement each precision can deliver (>= 99.5 % fp16/tf32, >= 98 % bf16);
-the measured agreement is printed and recorded in DESIGN.md."""
-# per-precision gates: (min top-1 agreement, max |d correct| in samples, max |d mean loss|)
-GATES = {"f32": (0.999, 0, 1e-5), "f16x3": (0.999, 1, 2e-5), "tf32": (0.995, 4, 2e-3), "f16": (0.995, 4, 2e-3), "bf16": (0.98, 12, 1e-2)}
+1e-3 absolute.  The PARITY modes -- f32 (fp32 operands, CUDA cores), f16x3 (fp16 hi/lo planes, three
+tensor-core passes) and f16c8 (fp16 pass + e4m3 compensation passes; the library default) -- are
+held to ALL of them.  The single-pass THROUGHPUT modes round GEMM operands to 11 (fp16, tf32) or 8
+(bf16) significant bits; on these RANDOM-INIT weights the 1st-percentile top-1 margin is ~0.006
+(SURVEY.md section 0), which is below what such an operand can resolve: they are held to the
+logit / loss / Shapley tolerances only, and their top-1 agreement is REPORTED (printed), not gated."""
+# per-precision gates: (min top-1 agreement, max |d correct| in samples, max |d mean loss|); None = reported only
+PARITY_MODES = ("f32", "f16x3", "f16c8")
+GATES = {"f32": (0.999, 0, 1e-5), "f16x3": (0.999, 1, 2e-5), "f16c8": (0.999, 1, 1e-4),
+         "tf32": (None, None, 2e-3), "f16": (None, None, 2e-3), "bf16": (None, None, 1e-2)}
 import pytest
 import torch
 
@@ -18,9 +21,9 @@ from oracle import restate
 
 pytestmark = pytest.mark.gpu
 
-PRECS = ["f32", "f16x3", "tf32", "f16", "bf16"]
+PRECS = ["f32", "f16x3", "f16c8", "tf32", "f16", "bf16"]
 # max |dlogit| vs the fp32 oracle that each operand precision is expected to stay under
-LOGIT_TOL = {"f32": 2e-4, "f16x3": 2e-4, "tf32": 1.5e-2, "f16": 1.5e-2, "bf16": 8e-2}
+LOGIT_TOL = {"f32": 2e-4, "f16x3": 2e-4, "f16c8": 5e-4, "tf32": 1.5e-2, "f16": 1.5e-2, "bf16": 8e-2}
 
 
 def make_engine(cfg, w0, deltas, images, labels, prec, **kw):
@@ -53,8 +56,9 @@ def test_forward_logits_small(prec):
         sd = restate.coalition_state_dict(w0, deltas, n_train, list(S))
         want = restate.vit_forward(sd, cfg, images)
         worst = max(worst, (logits[ci] - want).abs().max().item())
+        if prec in PARITY_MODES:
+            assert abs(int(correct[ci]) - int((want.argmax(1) == labels).sum())) <= GATES[prec][1]
         if prec == "f32":
-            assert int(correct[ci]) == int((want.argmax(1) == labels).sum())
             ce = torch.nn.functional.cross_entropy(want.double(), labels, reduction="sum").item()
             assert loss[ci] == pytest.approx(ce, rel=1e-5)
     print(f"[{prec}] max |dlogit| = {worst:.3e}")
@@ -89,17 +93,20 @@ def test_cfg1_against_reference_fixture(prec):
         u = game.eval_utility(S)
         pred = logits[ci].argmax(1).numpy()
         agree.append(float((pred == arr["pred"][ci]).mean()))
-        assert abs(u[0] - arr["utility"][ci, 0]) <= GATES[prec][1] / n + 1e-12
+        if GATES[prec][1] is not None:
+            assert abs(u[0] - arr["utility"][ci, 0]) <= GATES[prec][1] / n + 1e-12
         assert abs(u[1] - arr["utility"][ci, 1]) < GATES[prec][2]
-    print(f"[{prec}] min top-1 agreement over 15 coalitions = {min(agree):.4f}")
-    assert min(agree) >= GATES[prec][0]
+    print(f"[{prec}] min top-1 agreement over 15 coalitions = {min(agree):.4f}"
+          + ("" if GATES[prec][0] else "  (throughput mode: reported, not gated)"))
+    if GATES[prec][0] is not None:
+        assert min(agree) >= GATES[prec][0]
     ref = meta["estimators"]["exact"]
     err = max(abs(a - b) for got, want in zip(sv_lists(sv), ref) for a, b in zip(got, want))
     print(f"[{prec}] max |dShapley| = {err:.3e}")
     assert err < 1e-3
 
 
-@pytest.mark.parametrize("prec", ["f32", "f16x3", "f16"])
+@pytest.mark.parametrize("prec", ["f32", "f16x3", "f16c8", "f16"])
 def test_vit_base_geometry_against_reference_fixture(prec):
     """ViT-B/16 @ 224 (T = 197, 12 heads): logits for three coalitions vs the reference's."""
     meta, arr = load_golden("base_probe")
@@ -112,7 +119,7 @@ def test_vit_base_geometry_against_reference_fixture(prec):
     assert err < LOGIT_TOL[prec]
 
 
-@pytest.mark.parametrize("prec", ["f32", "f16x3", "f16", "bf16"])
+@pytest.mark.parametrize("prec", ["f32", "f16x3", "f16c8", "f16", "bf16"])
 def test_vit_large_geometry_against_oracle(prec):
     """ViT-L/16 @ 224 (h = 1024, 16 heads, ff = 4096; BASELINE config 4 runs it in bf16), 2 layers,
     3 clients: logits of three coalitions vs oracle/restate.py."""
@@ -151,9 +158,10 @@ def test_chunking_and_batching_do_not_change_results():
     cfg, w0, _, deltas, n_train, images, labels = synthetic_game(n_clients=3, n_val=200, layers=2, seed=2)
     coalitions = [(0,), (1,), (2,), (0, 1), (0, 2), (1, 2), (0, 1, 2)]
     rows = ratio_rows(coalitions, n_train)
-    a = make_engine(cfg, w0, deltas, images, labels, "f16", coalition_batch=7, image_chunk=200).evaluate(rows)
-    b = make_engine(cfg, w0, deltas, images, labels, "f16", coalition_batch=2, image_chunk=64).evaluate(rows)
-    assert a == b
+    for prec in ("f16", "f16c8"):
+        a = make_engine(cfg, w0, deltas, images, labels, prec, coalition_batch=7, image_chunk=200).evaluate(rows)
+        b = make_engine(cfg, w0, deltas, images, labels, prec, coalition_batch=2, image_chunk=64).evaluate(rows)
+        assert a == b
 
 
 def test_module_forward_and_evaluation_api():

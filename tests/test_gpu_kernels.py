@@ -96,6 +96,39 @@ def test_aggregate_16bit_is_rounded_fp32_result(ops, dtype, N, C):
     assert ((got.float() - want.float()).abs() <= ulp * want.float().abs() + 2.0 ** -24).all()
 
 
+@pytest.mark.parametrize("N,C,P", [(8, 8, 100_000), (3, 5, 1027), (16, 17, 70_001), (32, 16, 40_003)])
+@pytest.mark.parametrize("fmt_name", ["x3", "c8"])
+def test_aggregate_split_planes_are_the_split_of_the_fp32_result(ops, fmt_name, N, C, P):
+    """svit_aggregate_split: the planes are the exact split of the bit-exact fp32 aggregate (two-rounding arithmetic),
+    also at a column offset of a wider array and through the per-coalition base of the multi-round fold."""
+    from shapley_vit_b200._lib import FMT_C8, FMT_X3
+    from shapley_vit_b200.ops import OperandArray
+
+    fmt = FMT_X3 if fmt_name == "x3" else FMT_C8
+    rng = np.random.RandomState(N + C)
+    deltas, w0 = (gen(N, (P + 7) // 8 * 8, seed=P) * 0.02).cuda(), (gen((P + 7) // 8 * 8, seed=P + 1) * 0.02).cuda()
+    rows = fedavg_rows([rng.rand(N) < 0.5 for _ in range(C - 1)] + [np.ones(N, bool)], [1000 * (j + 1) for j in range(N)])
+    r = torch.tensor(rows, dtype=torch.float32)
+    ref = ops.aggregate(deltas, w0, r, P=P)[:, :P].cpu()                  # fp32, bit-exact vs the oracle (test above)
+    width, col0 = (P + 63) // 64 * 64 + 64, 64
+    out = OperandArray((C + 1, width), torch.float16, fmt, "cuda:0")
+    out.buf.zero_()
+    ops.aggregate(deltas, w0, r, out=out, P=P, col0=col0)
+    got = OperandArray((C, P), torch.float16, fmt, "cuda:0")
+    for k in range(2 if fmt == FMT_X3 else 3):
+        got.plane(k).copy_(out.plane(k)[:C, col0:col0 + P])
+        assert torch.count_nonzero(out.plane(k)[:C, :col0].view(torch.uint8)) == 0      # nothing outside the window
+        assert torch.count_nonzero(out.plane(k)[C].view(torch.uint8)) == 0
+    check_planes(got, ref, 0.0, exact=True)
+    base = (gen(C, (P + 7) // 8 * 8, seed=77) * 0.02).cuda()
+    ref2 = ops.aggregate_onto(deltas, base, r, torch.empty((C, (P + 7) // 8 * 8), device="cuda"), P=P)[:, :P].cpu()
+    out2 = OperandArray((C, (P + 7) // 8 * 8), torch.float16, fmt, "cuda:0")
+    ops.aggregate_onto(deltas, base, r, out2, P=P)
+    for k in range(2 if fmt == FMT_X3 else 3):
+        got.plane(k).copy_(out2.plane(k)[:, :P])
+    check_planes(got, ref2, 0.0, exact=True)
+
+
 def test_aggregate_rejects_misaligned(ops):
     from shapley_vit_b200._lib import SvitError
 
@@ -139,6 +172,10 @@ def test_layernorm(ops, h):
     for dt in (torch.bfloat16, torch.float16):
         got = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-12, out_dtype=dt).cpu()
         assert (got.float() - want).abs().max() < (4e-2 if dt == torch.bfloat16 else 5e-3)
+    from shapley_vit_b200._lib import FMT_C8, FMT_X3
+    for fmt, tol in ((FMT_X3, 2e-5), (FMT_C8, 4e-4)):        # the planes LayerNorm emits for the split precisions
+        y = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-12, fmt=fmt)
+        check_planes(y, want, tol)
 
 
 @pytest.mark.parametrize("image", [32, 224])
@@ -149,9 +186,17 @@ def test_patchify(ops, image):
     cfg = layout.vit_preset("tiny", image=image, n_cls=10, layers=1)
     img = gen(5, 3, image, image, seed=image)
     plan = ops.Plan(cfg, PREC_F32, 1, 5, "cuda:0")
-    got = plan.patchify(img.cuda()).cpu()
+    got = plan.patchify(img.cuda()).buf.cpu()
     want = F.unfold(img, kernel_size=16, stride=16).transpose(1, 2).reshape(-1, 768)
     assert torch.equal(got, want)
+    from shapley_vit_b200._lib import PRECISIONS
+    for name in ("f16x3", "f16c8"):                           # planes, written at a row offset of a larger matrix
+        plan = ops.Plan(cfg, PRECISIONS[name], 1, 5, "cuda:0")
+        arr = plan.operand_array((7 * cfg.n_patches, 768))
+        arr.buf.zero_()
+        plan.patchify(img.cuda(), out=arr, row0=2 * cfg.n_patches)
+        full = torch.cat([torch.zeros(2 * cfg.n_patches, 768), want])
+        check_planes(arr, full, 4e-4 if name == "f16c8" else 2e-6)
 
 
 @pytest.mark.parametrize("T,heads,d", [(5, 3, 64), (197, 12, 64), (197, 2, 32), (50, 2, 128), (16, 2, 64), (17, 1, 64),
@@ -172,17 +217,24 @@ def test_attention_fp32(ops, T, heads, d):
 
 
 @pytest.mark.parametrize("T,heads,n_seq", [(5, 3, 4), (197, 12, 9), (16, 2, 3), (17, 1, 3), (64, 3, 3), (208, 2, 3),
-                                           (209, 1, 3), (256, 1, 5)])
-def test_attention_f16x3(ops, T, heads, n_seq):
-    """Split-precision tensor-core attention (fp32 in / out, hi*hi + hi*lo + lo*hi): fp32-grade against fp64."""
+                                           (209, 1, 3), (256, 1, 5), (129, 2, 7), (160, 1, 3), (161, 3, 2), (224, 2, 200),
+                                           (225, 1, 3), (197, 12, 160)])
+@pytest.mark.parametrize("fmt_name", ["x3", "c8"])
+def test_attention_split(ops, T, heads, n_seq, fmt_name):
+    """Split-precision attention (X3 planes in, hi*lo + lo*hi + hi*hi on the tensor cores -- tcgen05 for
+    128 < T <= 224, mma.sync otherwise): fp32-grade against fp64; the context planes in either split format."""
+    from shapley_vit_b200._lib import FMT_C8, FMT_X3
+
     d, h = 64, heads * 64
     qkv = gen(n_seq, T, 3 * h, seed=T + 1)
     q, k, v = (t.double().view(n_seq, T, heads, d).transpose(1, 2) for t in qkv.split(h, dim=2))
     want = (torch.softmax(q @ k.transpose(2, 3) * d ** -0.5, dim=-1) @ v).transpose(1, 2).reshape(n_seq, T, h)
-    got = ops.attention_f16x3(qkv.cuda(), heads).cpu().double()
-    err = (got - want).abs().max().item()
-    print(f"attention f16x3 T={T}: max err {err:.3e}")
-    assert err < 1e-5
+    ctx = ops.attention_split(qkv.cuda(), heads, FMT_X3 if fmt_name == "x3" else FMT_C8)
+    if fmt_name == "x3":
+        err = (ctx.to_float().cpu().double() - want).abs().max().item()
+        print(f"attention split T={T}: max err {err:.3e}")
+        assert err < 1e-5
+    check_planes(ctx, want.float(), 1e-5 if fmt_name == "x3" else 4e-4, value_tol=1e-5)
 
 
 @pytest.mark.parametrize("T,heads,n_seq", [(197, 12, 40), (129, 3, 5), (256, 2, 7), (144, 1, 300), (250, 4, 3)])
@@ -263,7 +315,7 @@ def test_gemm_tcgen05_matches_cuda_core_gemm(ops, prec_name, G, M, N, K, monkeyp
 @pytest.mark.parametrize("G,M,N,K", [(1, 128, 256, 64), (2, 300, 768, 768), (1, 1000, 768, 3072), (2, 6000, 768, 256),
                                      (3, 197 * 4, 2304, 768), (2, 640, 576, 192), (2, 257, 512, 128)])
 def test_gemm_f16x3_split_precision(ops, G, M, N, K):
-    """SVIT_PREC_F16X3: fp32 operands split into fp16 hi + lo, three tcgen05 passes.  Held against the
+    """SVIT_PREC_F16X3: operands as fp16 hi + lo planes, three tcgen05 passes.  Held against the
     fp64 product of the UNROUNDED fp32 operands: >= 8x closer than one fp16 pass can be (measured 15-80x).
     What is left is the tensor core's own fp32 accumulation, which truncates (round toward zero) at every
     16-deep step: a bias that grows like K^1.5 on these all-positive-variance inputs."""
@@ -280,13 +332,93 @@ def test_gemm_f16x3_split_precision(ops, G, M, N, K):
     assert err < max(1e-5, 4e-6 * (K / 64) ** 1.5) and err < one_pass / 8
 
 
-def test_split_f16_halves(ops):
-    x = torch.cat([gen(2, 37, 64, seed=1), gen(2, 37, 64, seed=2) * 1e-3], dim=2)
-    got = ops.split_f16(x.cuda()).cpu()
-    K = x.shape[2]
-    hi = x.half()
-    lo = (x - hi.float()).half()
-    assert torch.equal(got[..., :K], hi) and torch.equal(got[..., K:], lo)
+def c8_emulation(A, B):
+    """fp64 value of the F16C8 product of fp32 A [G, M, K], B [G, N, K]: hi*hi + 2^-15 (hi8*lo8 + lo8*hi8)."""
+    def parts(x):
+        hi = x.half().float()
+        hi8 = (hi * 4.0).clamp(-448, 448).to(torch.float8_e4m3fn).double()
+        lo8 = ((x - hi) * 8192.0).clamp(-448, 448).to(torch.float8_e4m3fn).double()
+        return hi.double(), hi8, lo8
+    ah, a8, al = parts(A)
+    bh, b8, bl = parts(B)
+    t = lambda x: x.transpose(1, 2)
+    return ah @ t(bh) + (a8 @ t(bl) + al @ t(b8)) / 32768.0
+
+
+@pytest.mark.parametrize("G,M,N,K", [(1, 128, 256, 128), (2, 300, 768, 768), (1, 1000, 768, 3072), (2, 6000, 768, 256),
+                                     (3, 197 * 4, 2304, 768), (2, 640, 576, 192), (2, 257, 512, 128)])
+def test_gemm_f16c8_compensated(ops, G, M, N, K):
+    """SVIT_PREC_F16C8: fp16 main pass + two e4m3 compensation passes (kind::f8f6f4) folded in with scale-input-d.
+    (1) the kernel computes exactly the emulated sum (same planes, fp64 arithmetic) up to the tensor core's fp32
+    accumulation; (2) that sum is >= 8x closer to the unrounded product than one fp16 pass (measured ~25x)."""
+    from shapley_vit_b200._lib import PRECISIONS
+
+    A, B = gen(G, M, K, seed=M), gen(G, N, K, seed=N) * 0.05
+    bias, res = gen(G, N, seed=3), gen(G, M, N, seed=4)
+    got = ops.gemm(PRECISIONS["f16c8"], A.cuda(), B.cuda(), bias=bias.cuda(), residual=res.cuda(),
+                   out_dtype=torch.float32).cpu().double()
+    want = ref_gemm(A, B, bias, res)
+    emu = c8_emulation(A, B) + bias.double().unsqueeze(1) + res.double()
+    err, err_emu = (got - want).abs().max().item(), (got - emu).abs().max().item()
+    one_pass = (ref_gemm(A.half().float(), B.half().float(), bias, res) - want).abs().max().item()
+    print(f"f16c8 max err {err:.3e} vs exact, {err_emu:.3e} vs emulation (one fp16 pass: {one_pass:.3e})")
+    assert err_emu < max(1e-5, 4e-6 * (K / 64) ** 1.5)
+    assert err < one_pass / 8
+
+
+@pytest.mark.parametrize("prec_name", ["f16x3", "f16c8"])
+def test_gemm_split_plane_outputs(ops, prec_name):
+    """The 16-bit output of a split-precision GEMM is a packed operand array written by the epilogue (QKV, GELU(MLP-up)):
+    pair kernel (M >= 256) and 1-CTA kernel (M < 256), with and without GELU."""
+    from shapley_vit_b200._lib import PRECISIONS
+
+    prec = PRECISIONS[prec_name]
+    for (G, M, N, K, gelu) in ((2, 394, 768, 256, False), (2, 394, 3072, 256, True), (3, 128, 768, 128, True), (1, 60, 256, 128, False)):
+        A, B, bias = gen(G, M, K, seed=M + N), gen(G, N, K, seed=N) * 0.05, gen(G, N, seed=9)
+        out = ops.gemm(prec, A.cuda(), B.cuda(), bias=bias.cuda(), gelu=gelu, out_dtype=torch.float16)
+        want = ref_gemm(A, B, bias, gelu=gelu).float()
+        check_planes(out, want, 2e-4 if prec_name == "f16c8" else 3e-5, value_tol=3e-4 if prec_name == "f16c8" else 3e-5)
+
+
+def test_split_operand_planes(ops):
+    from shapley_vit_b200._lib import FMT_C8, FMT_X3
+    from shapley_vit_b200.ops import OperandArray
+
+    x = torch.cat([gen(2, 37, 64, seed=1), gen(2, 37, 64, seed=2) * 1e-3, gen(2, 37, 64, seed=3) * 30], dim=2)
+    for fmt in (FMT_X3, FMT_C8):
+        arr = OperandArray.from_float(x.cuda(), fmt)
+        check_planes(arr, x, 0.0, exact=True)
+
+
+def check_planes(arr, want, tol, value_tol=None, exact=False):
+    """`arr` (OperandArray, split format) against the fp32 tensor `want` it should stand for: every plane must be the
+    split of ONE fp32 value v with |v - want| <= value_tol (default tol): hi = fp16(v), lo = fp16(v - hi) (X3) or
+    hi8 = e4m3(4 hi), lo8 = e4m3(8192 (v - hi)) (C8)."""
+    from shapley_vit_b200._lib import FMT_X3
+
+    want = want.float().reshape(arr.shape)
+    hi = arr.plane(0).cpu().float()
+    if arr.fmt == FMT_X3:
+        lo = arr.plane(1).cpu().float()
+        v = hi + lo
+        if exact:
+            assert torch.equal(hi, want.half().float()) and torch.equal(lo, (want - want.half().float()).half().float())
+            return
+        assert (v - want).abs().max() <= (value_tol if value_tol is not None else tol)
+        assert torch.equal(hi, v.half().float()) or (hi - v.half().float()).abs().max() <= 2 ** -10 * want.abs().max()
+    else:
+        hi8, lo8 = arr.plane(1).cpu().float(), arr.plane(2).cpu().float()
+        want_hi8 = (hi * 4.0).clamp(-448, 448).to(torch.float8_e4m3fn).float()
+        assert torch.equal(hi8, want_hi8)                                 # hi8 is a function of hi alone
+        if exact:
+            h = want.half().float()
+            assert torch.equal(hi, h)
+            assert torch.equal(lo8, ((want - h) * 8192.0).clamp(-448, 448).to(torch.float8_e4m3fn).float())
+            return
+        assert (hi - want).abs().max() <= 2 ** -10 * want.abs().max() + (value_tol if value_tol is not None else tol)
+        # lo8 carries the residual to ~4 bits: |hi + lo8 / 8192 - want| <= residual / 8 + value_tol
+        resid = (want - hi).abs()
+        assert ((hi + lo8 / 8192.0 - want).abs() <= resid / 8 + 2 ** -10 / 8192 + (value_tol if value_tol is not None else tol)).all()
 
 
 @pytest.mark.parametrize("prec_name", ["f16", "tf32"])
