@@ -52,10 +52,11 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-images", type=int, default=48)
+    ap.add_argument("--cpu-sample-images", type=int, default=256)
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-throughput-mode", action="store_true")
     ap.add_argument("--parity-clients", type=int, default=4)
-    ap.add_argument("--parity-images", type=int, default=256)
+    ap.add_argument("--parity-images", type=int, default=10000)
     return ap.parse_args()
 
 
@@ -128,10 +129,16 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the reference's own path, restated (oracle/restate.py) around the
-# reference's actual third-party model (HF ViTForImageClassification, fp32 eager)
+# CPU baseline / reference arm: the reference's OWN Game.eval_utility + evaluation (oracle/ref_arm.py drives the
+# unmodified reference classes, staged by build() into oracle/_ref for the GPU box) around the reference's actual
+# third-party model (HF ViTForImageClassification, fp32 eager).  Falls back to the restatement (oracle/restate.py,
+# kind "port") only when neither /root/reference nor oracle/_ref exists.
 # ----------------------------------------------------------------------------------------------
-class CpuPath:
+class PortPath:
+    """The restated path (oracle/restate.py) -- used only when the reference itself cannot be imported."""
+
+    kind = "port"
+
     def __init__(self, a):
         import torch
 
@@ -153,12 +160,13 @@ class CpuPath:
         self.images, self.labels = synth.make_val_set(self.cfg, self.n_img, a.seed)
         self.model = build_hf_vit(self.cfg, self.w0)
         self.coalitions = list(restate.powerset(range(a.clients)))
-        self.sample = (f"1 coalition per step: full-size FedAvg aggregation + load_state_dict, forward/score on "
-                       f"{self.n_img} of {a.val} images (HF ViT fp32 eager, batch 128), extrapolated linearly in images")
+        self.sample = (f"restated path (oracle/restate.py), 1 coalition per step: full-size FedAvg aggregation + load_state_dict, "
+                       f"forward/score on {self.n_img} of {a.val} images (HF ViT fp32 eager, batch 128), scaled linearly in images")
 
-    def step(self, i: int) -> float:
+    def step(self, i: int, warm: bool = False) -> float:
         """Seconds one full coalition evaluation would take (measured on the sample, extrapolated)."""
         torch, restate = self.torch, self.restate
+        n_img = min(16, self.n_img) if warm else self.n_img
         S = self.coalitions[(37 * i + len(self.coalitions) // 2) % len(self.coalitions)]
         t0 = time.perf_counter()
         members = restate.reference_member_order(S)
@@ -167,22 +175,35 @@ class CpuPath:
         t_agg = time.perf_counter() - t0
         t0 = time.perf_counter()
         correct, loss = 0, 0.0
-        for s in range(0, self.n_img, 128):                  # evaluation(), utils.py:864-926 (autograd on)
-            out = self.model(self.images[s:s + 128]).logits
+        for s in range(0, n_img, 128):                  # evaluation(), utils.py:864-926 (autograd on)
+            out = self.model(self.images[s:min(s + 128, n_img)]).logits
             pred = out.argmax(dim=1)
-            correct += pred.eq(self.labels[s:s + 128]).sum().item()
-            loss += torch.nn.functional.cross_entropy(out, self.labels[s:s + 128], reduction="sum").item()
+            correct += pred.eq(self.labels[s:min(s + 128, n_img)]).sum().item()
+            loss += torch.nn.functional.cross_entropy(out, self.labels[s:min(s + 128, n_img)], reduction="sum").item()
         t_fwd = time.perf_counter() - t0
-        return t_agg + t_fwd * (self.a.val / self.n_img)
+        return t_agg + t_fwd * (self.a.val / n_img)
+
+
+def make_cpu_path(a):
+    from oracle import ref_shim
+
+    if ref_shim.available():
+        from oracle.ref_arm import ReferenceArm
+        from shapley_vit_b200 import layout
+
+        arm = ReferenceArm(layout.vit_preset(a.vit, image=a.image, n_cls=a.classes), a.clients, a.val, a.cpu_sample_images, a.seed)
+        arm.kind = "reference"
+        return arm
+    return PortPath(a)
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cpu = CpuPath(a)
+    cpu = make_cpu_path(a)
     for i in range(a.warmup):
-        cpu.step(i)
+        cpu.step(i, warm=True)
     t0 = time.perf_counter()
     per = [cpu.step(a.warmup + i) for i in range(a.steps)]
     wall = time.perf_counter() - t0
@@ -192,40 +213,67 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * wall / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "step": "one coalition evaluation on a bounded sample, extrapolated",
-                   "device": "host CPU"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": cpu.sample},
+        "config": {"workload": workload_name(a), "step": "one coalition evaluation on a bounded sample, scaled linearly in images",
+                   "device": "host CPU", "reference_root": getattr(cpu, "ref_root", None)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_subprocess(a):
+    """The same arm in a child process that sees no GPU (the reference would otherwise move its models to
+    cuda:1 / cuda:0, server2.py:17, utils.py:865): one warm-up step and one timed step."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--vit", a.vit, "--image", str(a.image), "--classes", str(a.classes), "--clients", str(a.clients),
+           "--val", str(a.val), "--seed", str(a.seed), "--cpu-sample-images", str(a.cpu_sample_images)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    for ln in reversed(r.stdout.splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    return {"error": (r.stderr or r.stdout)[-400:]}
+
+
 # ----------------------------------------------------------------------------------------------
-def parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev):
-    """The second half of the metric ("Shapley abs err"): exact Shapley of a reduced game (first
-    `--parity-clients` clients, first `--parity-images` validation images, every coalition) computed in
-    the benchmarked precision and in the library's fp32 mode (fp32 operands, CUDA-core GEMMs -- the mode
-    the GPU tests hold to the oracle at 100 % top-1 agreement and 4e-8 Shapley error), on the same
-    device buffers.  Returns max |d Shapley|, the per-coalition top-1 agreement and the utility gap."""
+def parity_leg(a, cfg, lay, deltas, w0, images_host, labels_host, dev, val_main=None):
+    """The second half of the metric ("Shapley abs err") and north_star's gates (>= 99.9 % top-1 agreement per
+    coalition, utilities within one sample, Shapley within 1e-3), on the bench's own device buffers.
+
+    (1) The exact-Shapley game of the first `--parity-clients` clients (every coalition) over `--parity-images`
+        validation images (default: all 10 000, i.e. >= 10 000 predictions per coalition) in the benchmarked
+        precision and in an fp32-grade mode (`f16x3`: fp16 hi+lo operands, three tcgen05 passes, logits within
+        ~1e-5 of fp32; `f16c8` when f16x3 itself is benchmarked): top-1 agreement, utility gap, Shapley gap.
+    (2) anchor_f32: the same coalitions on the first 256 images in the library's fp32 mode (fp32 operands,
+        CUDA-core FMA GEMMs) against every mode of (1).
+    (3) anchor_oracle: two coalitions x 64 images through the CPU restatement of the reference path
+        (oracle/restate.py: the reference's aggregation order + the HF ViT forward, pinned on reference outputs by
+        tests/golden) against every mode: max |dlogit| and top-1 agreement.  The oracle is the checker here."""
     import torch
 
-    from shapley_vit_b200 import synth
+    from shapley_vit_b200 import layout, synth
     from shapley_vit_b200.engine import CoalitionEngine
     from shapley_vit_b200.estimators import powerset, shapley_exact
     from shapley_vit_b200.fl import ClientBase, ServerBase
     from shapley_vit_b200.game import Game
 
     n_c, n_img = min(a.parity_clients, a.clients), min(a.parity_images, a.val)
-    images, labels = images_host[:n_img], labels_host[:n_img]
+    n_head = min(256, n_img)
     n_train = synth.client_sizes(a.clients)[:n_c]
     coalitions = list(powerset(range(n_c)))
-    sv, preds, util = {}, {}, {}
+    d_sub = deltas[:n_c].contiguous()
     t0 = time.perf_counter()
-    gate = "f16c8" if a.precision in ("f16", "bf16", "tf32") else None   # the tensor-core mode that meets the top-1 gate
-    for prec in [x for x in (a.precision, gate, "f32") if x]:
-        eng = CoalitionEngine(cfg, w0, deltas[:n_c].contiguous(), images, labels, precision=prec, coalition_batch=5,
-                              image_chunk=min(32, n_img), device=dev, keep_logits=True)
+    throughput_mode = a.precision in ("f16", "bf16", "tf32")
+    ref_mode = "f16c8" if a.precision == "f16x3" else "f16x3"
+    modes = [a.precision] + (["f16c8"] if throughput_mode else []) + ([ref_mode] if a.precision != "f32" else [])
+    sv, preds, util, head = {}, {}, {}, {}
+
+    def run(prec, images, labels, cb, chunk, val=None):
+        eng = CoalitionEngine(cfg, w0, d_sub, val if val is not None else images, labels, precision=prec, coalition_batch=cb,
+                              image_chunk=chunk, device=dev, keep_logits=True)
         clients = [ClientBase(i, {}, None, synth.SizedStub(n)) for i, n in enumerate(n_train)]
         server = ServerBase({}, None, clients, None, eng.val, None)
         rows = []
@@ -235,33 +283,74 @@ def parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev):
             for j, v in zip(S, r):
                 row[j] = v
             rows.append(row)
-        p = []
-        for s0 in range(0, len(rows), 5):
-            eng.evaluate(rows[s0:s0 + 5])
-            p.append(eng.last_logits.argmax(dim=2).cpu())
-        preds[prec] = torch.cat(p)
         game = Game(clients, server, None, [None] * n_c, [True] * n_c, [0.0, 0.0], 2, {"precision": prec})
-        game._engine = eng
+        p, lg, counts = [], [], ([], [])
+        for s0 in range(0, len(rows), cb):
+            c, l = eng.evaluate(rows[s0:s0 + cb])
+            counts[0].extend(c), counts[1].extend(l)
+            p.append(eng.last_logits.argmax(dim=2).cpu())
+            lg.append(eng.last_logits[:, :n_head].cpu())
+        n = eng.n_val
+        for S, c, l in zip(coalitions, *counts):       # fill the memo from the evaluation above: no second pass
+            game.utility[0][frozenset(S)] = c / n
+            game.utility[1][frozenset(S)] = l / n
         phi = shapley_exact(game)
-        sv[prec] = [[phi[d][c] for c in range(n_c)] for d in range(2)]
-        util[prec] = [game.eval_utility(S) for S in coalitions]
-        del eng, game
+        del eng
         torch.cuda.empty_cache()
-    ref = "f32"
-    err = max(abs(x - y) for d in range(2) for x, y in zip(sv[a.precision][d], sv[ref][d]))
-    agree = (preds[a.precision] == preds[ref]).float().mean(dim=1)
-    du = max(abs(u[0] - v[0]) for u, v in zip(util[a.precision], util[ref]))
-    out = {"shapley_abs_err": err, "top1_agreement_min": float(agree.min()), "top1_agreement_mean": float(agree.mean()),
-           "accuracy_utility_abs_err_max": du, "reference": "this library's fp32 mode (held to the CPU oracle in tests/test_gpu_forward.py)",
-           "game": f"{n_c} clients, {len(coalitions)} coalitions, {n_img} images, {a.vit} @ {a.image}px, exact Shapley"}
-    if gate:
-        ag = (preds[gate] == preds[ref]).float().mean(dim=1)
-        out["gate_mode"] = {
-            "precision": gate, "shapley_abs_err": max(abs(x - y) for d in range(2) for x, y in zip(sv[gate][d], sv[ref][d])),
-            "top1_agreement_min": float(ag.min()), "top1_agreement_mean": float(ag.mean()),
-            "accuracy_utility_abs_err_max": max(abs(u[0] - v[0]) for u, v in zip(util[gate], util[ref])),
-            "note": "split-precision tensor-core mode (fp16 hi/lo operands, 3 MMA passes): `python bench.py --precision f16x3`, "
-                    "measured line in profiles/r1_bench_f16x3.json"}
+        return ([[phi[d][c] for c in range(n_c)] for d in range(2)], torch.cat(p), [game.eval_utility(S) for S in coalitions],
+                torch.cat(lg))
+
+    for prec in modes:
+        reuse = val_main if (val_main is not None and prec == a.precision and n_img == a.val) else None
+        sv[prec], preds[prec], util[prec], head[prec] = run(prec, images_host[:n_img], labels_host[:n_img], 8, 128, reuse)
+
+    def versus(m, r, sl=slice(None)):
+        agree = (preds[m][:, sl] == preds[r][:, sl]).float().mean(dim=1)
+        return {"shapley_abs_err": max(abs(x - y) for d in range(2) for x, y in zip(sv[m][d], sv[r][d])),
+                "top1_agreement_min": float(agree.min()), "top1_agreement_mean": float(agree.mean()),
+                "accuracy_utility_abs_err_max": max(abs(u[0] - v[0]) for u, v in zip(util[m], util[r]))}
+
+    out = {}
+    if a.precision != "f32":
+        out.update(versus(a.precision, ref_mode))
+        out.update({"predictions_per_coalition": n_img, "one_sample": 1.0 / n_img,
+                    "reference": f"this library's {ref_mode} mode on the same {n_img} images (fp32-grade split-precision tensor-core mode), "
+                                 "itself anchored to the fp32 CUDA-core mode (anchor_f32) and to the CPU oracle (anchor_oracle)",
+                    "game": f"{n_c} clients, {len(coalitions)} coalitions, {n_img} images, {a.vit} @ {a.image}px, exact Shapley"})
+        if throughput_mode:
+            out["gate_mode"] = dict(versus("f16c8", ref_mode), precision="f16c8",
+                                    note="the default precision (fp16 + e4m3-compensated tensor-core mode) on the same game")
+
+    # ---- (2) the fp32 CUDA-core mode on the first n_head images ------------------------------------
+    sv["f32"], preds["f32"], util["f32"], head["f32"] = run("f32", images_host[:n_head], labels_host[:n_head], 5, min(32, n_head))
+    anchor = {"images": n_head, "coalitions": len(coalitions)}
+    for m in modes:
+        agree = (preds[m][:, :n_head] == preds["f32"]).float().mean(dim=1)
+        anchor[m] = {"top1_agreement_min": float(agree.min()), "max_abs_dlogit": float((head[m] - head["f32"]).abs().max())}
+    out["anchor_f32"] = anchor
+
+    # ---- (3) the CPU oracle on two coalitions x 64 images ------------------------------------------
+    try:
+        from oracle import restate
+
+        n_or = min(64, n_head)
+        w0_sd = layout.unpack_row(lay, w0.cpu())
+        d_sds = [layout.unpack_row(lay, d_sub[j].cpu()) for j in range(n_c)]
+        picks = [0, len(coalitions) - 1] if len(coalitions) > 1 else [0]
+        orc = {"images": n_or, "coalitions": [list(coalitions[i]) for i in picks],
+               "oracle": "oracle/restate.py (reference aggregation order + HF ViT forward, fp32, CPU)"}
+        want = []
+        for i in picks:
+            sd = restate.coalition_state_dict(w0_sd, d_sds, n_train, restate.reference_member_order(coalitions[i]))
+            want.append(restate.vit_forward(sd, cfg, images_host[:n_or].float()))
+        want = torch.stack(want)
+        for m in modes + ["f32"]:
+            got = head[m][picks][:, :n_or]
+            orc[m] = {"max_abs_dlogit": float((got - want).abs().max()),
+                      "top1_agreement": float((got.argmax(2) == want.argmax(2)).float().mean())}
+        out["anchor_oracle"] = orc
+    except Exception as e:
+        out["anchor_oracle"] = {"error": repr(e)}
     out["seconds"] = time.perf_counter() - t0
     return out
 
@@ -438,10 +527,33 @@ def run_ours(a):
             td.destroy_process_group()
         return
 
-    parity = None
-    if ws == 1 and not a.no_parity and a.precision != "f32":
+    # ---- the single-pass fp16 throughput mode on the same workload (outside the top-1 gate; reported, not the headline)
+    throughput_mode = None
+    if ws == 1 and not a.no_throughput_mode and a.precision in ("f16c8", "f16x3"):
         try:
-            parity = parity_leg(a, cfg, deltas, w0, images_host, labels_host, dev)
+            p16 = _lib.PRECISIONS["f16"]
+            val16 = ValidationSet(cfg, images_host, labels_host, p16, dev)
+            eng16 = CoalitionEngine(cfg, w0, deltas, val16, precision=p16, coalition_batch=Cb, image_chunk=a.image_chunk, device=dev)
+            eng16._run_batch(rows_for(0, 0))
+            torch.cuda.synchronize(dev)
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for i in range(2):
+                eng16._run_batch(rows_for(a.warmup + i, 0))
+            t1e.record()
+            torch.cuda.synchronize(dev)
+            throughput_mode = {"precision": "f16", "value": 2 * Cb / (t0e.elapsed_time(t1e) / 1e3), "unit": UNIT, "steps": 2, "warmup": 1,
+                               "note": "single fp16 tcgen05 pass per product: ~99.2-99.7 % top-1 agreement with fp32 on random-init weights, "
+                                       "i.e. OUTSIDE north_star's 99.9 % gate; `python bench.py --precision f16` is the full line"}
+            del eng16, val16
+            torch.cuda.empty_cache()
+        except Exception as e:
+            throughput_mode = {"error": repr(e)}
+
+    parity = None
+    if ws == 1 and not a.no_parity:
+        try:
+            parity = parity_leg(a, cfg, lay, deltas, w0, images_host, labels_host, dev, val_main=val)
         except Exception as e:  # never lose the throughput line to the parity leg
             parity = {"error": repr(e)}
 
@@ -450,19 +562,25 @@ def run_ours(a):
     g_ms, g_flops, g_n = timing["gemm"]
     tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
-    # DRAM bytes per GEMM launch from the committed ncu --set full capture of this configuration
-    traffic, traffic_agg = None, None
-    if a.vit == "base" and a.coalition_batch == 8 and a.image_chunk == 128 and a.precision in ("f16", "bf16"):
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                tj = json.load(f)
-            traffic, traffic_agg = tj["gemm_avg_dram_bytes_per_launch"], tj["aggregate_dram_bytes_per_launch"]
-        except Exception:
-            pass
+    # DRAM bytes per launch: NOT measured in this run -- read from the committed `ncu --set full` capture of this
+    # configuration and precision (profiles/r2_traffic.json, else round 1's f16 capture)
+    traffic, traffic_agg, traffic_src = None, None, None
+    if a.vit == "base" and a.coalition_batch == 8 and a.image_chunk == 128:
+        for fn in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", fn)) as f:
+                    tj = json.load(f)
+                tj = tj.get(a.precision, tj if (fn.startswith("r1") and a.precision in ("f16", "bf16")) else None)
+                if tj:
+                    traffic, traffic_agg = tj["gemm_avg_dram_bytes_per_launch"], tj["aggregate_dram_bytes_per_launch"]
+                    traffic_src = f"profiles/{fn}: committed ncu --set full capture of this configuration (dram__bytes_read+write per launch), not this run"
+                    break
+            except Exception:
+                pass
     roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2 grouped GEMM)" if a.precision != "f32" else "gemm_simt_kernel",
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
                 "peak_source": f"{peak_src}; sustained figure (kernel timed inside a long step); burst = {peaks['bf16_tflops']}",
-                "traffic": traffic, "algorithmic_flops_per_launch": g_flops / max(g_n, 1),
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_flops_per_launch": g_flops / max(g_n, 1),
                 "launches": int(g_n), "avg_launch_ms": g_ms / max(g_n, 1),
                 "share_of_step": g_ms / elapsed_ms}
     if a.precision in ("f16x3", "f16c8"):
@@ -485,7 +603,7 @@ def run_ours(a):
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "launches": agg_launches,
                     "frac": (agg_bytes / (agg_ms / 1e3) / 1e9 / peaks["hbm_gbs"]) if agg_ms else None,
                     "algorithmic_bytes_per_step": agg_bytes / a.steps, "traffic": traffic_agg}
-    model_flops = cfg.flops_per_image() * a.val * Cb * a.steps
+    model_flops_nominal = cfg.flops_per_image() * a.val * Cb * a.steps     # HF forward, every token of every layer
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ws, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -493,20 +611,17 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "step": f"{Cb} coalitions per GPU: aggregate + forward over {a.val} images + score",
                    "coalition_batch": Cb, "image_chunk": a.image_chunk, "parallelism": f"coalition-sharded x{ws}",
                    "l2": "inputs per step (2.7 GB delta stack, 3 GB patch matrix) exceed the 126 MB L2; no flush needed",
-                   "model_tflops_per_s_per_gpu": model_flops / (elapsed_ms / 1e3) / 1e12},
+                   # executed GEMM + attention FLOPs (the last layer computes only the [CLS] rows past K and V)
+                   "model_tflops_per_s_per_gpu": (g_flops + a_flops) / (elapsed_ms / 1e3) / 1e12,
+                   "hf_equivalent_tflops_per_s_per_gpu": model_flops_nominal / (elapsed_ms / 1e3) / 1e12},
         "roofline": roofline, "roofline_aggregate": roofline_agg, "breakdown": breakdown,
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "throughput_mode": throughput_mode,
     }
     if ws == 1 and not a.no_cpu_baseline:
-        cpu = CpuPath(a)
-        cpu.step(0)
-        t0, per = time.perf_counter(), []
-        i = 1
-        while time.perf_counter() - t0 < 12.0 and i < 4:
-            per.append(cpu.step(i))
-            i += 1
-        sec = sum(per) / len(per)
-        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": cpu.sample}
+        try:
+            line["cpu_baseline"] = cpu_baseline_subprocess(a)
+        except Exception as e:  # never lose the throughput line to the CPU leg
+            line["cpu_baseline"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
     if ws > 1:
         td.destroy_process_group()
@@ -515,6 +630,7 @@ def run_ours(a):
 def main():
     a = parse_args()
     if a.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""   # the CPU arm: the reference would otherwise use cuda:1 / cuda:0
         run_reference(a)
     else:
         run_ours(a)

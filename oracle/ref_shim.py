@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *real* reference.
 
 Makes the reference's own hot-path modules importable from ``/root/reference``
-in the build container (they cannot travel to the GPU box).  Used by
+in the build container, or from the byte-for-byte staged copy ``oracle/_ref`` (``oracle/stage_ref.py``,
+git-ignored, travels with the gpurun snapshot) on the GPU box.  Used by ``bench.py``'s reference arm, by
 ``oracle/make_golden.py`` to generate the fixtures under ``tests/golden/`` and by
 the CPU tests that cross-check ``oracle/restate.py`` when the reference tree is
 present.  Nothing in the product package imports this file.
@@ -21,7 +22,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SVIT_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # written by oracle/stage_ref.py
+
+
+def _reference_root() -> str:
+    """$SVIT_REFERENCE_ROOT, else /root/reference (build container), else the staged copy oracle/_ref (GPU box)."""
+    env = os.environ.get("SVIT_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/shapleyserver/fed_client_contribution"):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def available() -> bool:
