@@ -14,7 +14,8 @@
  *   svit_patchify,
  *   svit_forward_batched  <- net(img).logits inside evaluation, federated_learning/utils.py:886
  *                            (HF ViTForImageClassification built at start.py:258-267)
- *   svit_score            <- argmax / correct / CrossEntropy(sum) in evaluation,
+ *   svit_score, svit_score_records
+ *                         <- argmax / correct / CrossEntropy(sum) in evaluation,
  *                            federated_learning/utils.py:891-894
  *   svit_plan_timing_*    <- (new) CUDA-event timing per kernel class; the reference only prints
  *                            'before net' / 'after net' (federated_learning/utils.py:885-887)
@@ -204,6 +205,17 @@ int svit_plan_timing_end(svit_plan* plan, svit_timing* out);
 int svit_score(const float* logits, int64_t logits_stride, const int64_t* labels, int C, int64_t n,
                int n_cls, int64_t* correct, double* loss_sum, int32_t* pred, int64_t pred_stride,
                int accumulate, svit_stream_t stream);
+
+/* The same scoring written as packed 16-byte records, the element of the multi-GPU exchange: a rank's K5 launches
+ * write its coalitions' records straight into its slot of the all-gather send buffer (one
+ * ncclAllGather of per-coalition (correct:int64, loss_sum:fp64) pairs per wave; no host round trip in between).
+ *   records device [C] svit_record, 16-byte aligned */
+typedef struct svit_record {
+  int64_t correct;
+  double loss_sum;
+} svit_record;
+int svit_score_records(const float* logits, int64_t logits_stride, const int64_t* labels, int C, int64_t n,
+                       int n_cls, svit_record* records, int accumulate, svit_stream_t stream);
 
 /* ---- building blocks (exported for per-kernel parity tests and roofline timing) ------ */
 typedef struct svit_epilogue {

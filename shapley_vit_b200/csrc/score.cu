@@ -21,8 +21,9 @@ constexpr int kScoreBlock = 256;
 __global__ void __launch_bounds__(kScoreBlock) score_kernel(const float* __restrict__ logits, int64_t logits_stride,
                                                             const int64_t* __restrict__ labels, int64_t n, int n_cls,
                                                             int64_t* __restrict__ correct,
-                                                            double* __restrict__ loss_sum, int32_t* __restrict__ pred,
-                                                            int64_t pred_stride, int accumulate) {
+                                                            double* __restrict__ loss_sum, int out_stride,
+                                                            int32_t* __restrict__ pred, int64_t pred_stride,
+                                                            int accumulate) {
   const int c = blockIdx.x;
   const float* lg = logits + (size_t)c * logits_stride;
   long long my_correct = 0;
@@ -76,12 +77,13 @@ __global__ void __launch_bounds__(kScoreBlock) score_kernel(const float* __restr
       tc += s_c[w];
       tl += s_l[w];
     }
+    const size_t o = (size_t)c * out_stride;  // 1: separate [C] arrays; 2: interleaved svit_record entries
     if (accumulate) {
-      correct[c] += tc;
-      loss_sum[c] += tl;
+      correct[o] += tc;
+      loss_sum[o] += tl;
     } else {
-      correct[c] = tc;
-      loss_sum[c] = tl;
+      correct[o] = tc;
+      loss_sum[o] = tl;
     }
   }
 }
@@ -98,8 +100,22 @@ extern "C" int svit_score(const float* logits, int64_t logits_stride, const int6
   SVIT_CHECK_ARG(logits_stride >= n * n_cls, "svit_score: logits_stride too small");
   SVIT_CHECK_ARG(!pred || pred_stride >= n, "svit_score: pred_stride too small");
   score_kernel<<<C, kScoreBlock, 0, static_cast<cudaStream_t>(stream)>>>(logits, logits_stride, labels, n, n_cls,
-                                                                         reinterpret_cast<int64_t*>(correct), loss_sum,
+                                                                         reinterpret_cast<int64_t*>(correct), loss_sum, 1,
                                                                          pred, pred_stride, accumulate);
+  SVIT_LAUNCH_CHECK("score_kernel");
+  return SVIT_OK;
+}
+
+extern "C" int svit_score_records(const float* logits, int64_t logits_stride, const int64_t* labels, int C, int64_t n,
+                                  int n_cls, svit_record* records, int accumulate, svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(logits && labels && records, "svit_score_records: null pointer");
+  SVIT_CHECK_ARG(C >= 1 && n >= 0 && n_cls >= 1, "svit_score_records: C=%d n=%lld n_cls=%d out of range", C, (long long)n, n_cls);
+  SVIT_CHECK_ARG(logits_stride >= n * n_cls, "svit_score_records: logits_stride too small");
+  if ((uintptr_t)records & 15) SVIT_FAIL(SVIT_ERR_ALIGN, "svit_score_records: records must be 16-byte aligned");
+  static_assert(sizeof(svit_record) == 16, "record layout");
+  score_kernel<<<C, kScoreBlock, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, logits_stride, labels, n, n_cls, &records->correct, &records->loss_sum, 2, nullptr, 0, accumulate);
   SVIT_LAUNCH_CHECK("score_kernel");
   return SVIT_OK;
 }

@@ -79,15 +79,22 @@ class ValidationSet:
 class CoalitionEngine:
     def __init__(self, cfg: VitConfig, w0, deltas, images, labels: Optional[torch.Tensor] = None,
                  precision: str = _lib.DEFAULT_PRECISION, coalition_batch: int = 8, image_chunk: int = 128,
-                 device: str | torch.device = "cuda:0", keep_logits: bool = False):
-        """``images`` is either a host tensor [n, C, H, W] (with ``labels``) or a ValidationSet."""
+                 device: str | torch.device = "cuda:0", keep_logits: bool = False, n_clients: Optional[int] = None):
+        """``images`` is either a host tensor [n, C, H, W] (with ``labels``) or a ValidationSet.
+        ``deltas=None`` (with ``n_clients``): no single-round stack is resident -- the engine serves the multi-round
+        mode (``set_round_deltas`` / ``evaluate_rounds``) and, for all-zero ratio rows, W_0 itself."""
         if not torch.cuda.is_available():
             raise RuntimeError("CoalitionEngine needs a CUDA device (sm_100a); there is no CPU path")
         self.cfg = cfg
         self.device = torch.device(device)
         self.lay: PlanLayout = plan_layout(cfg)
         self.precision = _lib.PRECISIONS[precision] if isinstance(precision, str) else int(precision)
-        self.n_clients = int(deltas.shape[0]) if isinstance(deltas, torch.Tensor) else len(deltas)
+        if deltas is None:
+            if n_clients is None:
+                raise ValueError("deltas=None needs n_clients")
+            self.n_clients = int(n_clients)
+        else:
+            self.n_clients = int(deltas.shape[0]) if isinstance(deltas, torch.Tensor) else len(deltas)
         if not 1 <= self.n_clients <= 64:
             raise ValueError("1..64 clients supported")
         self.n_val = images.n if isinstance(images, ValidationSet) else int(images.shape[0])
@@ -105,7 +112,10 @@ class CoalitionEngine:
             total = self.lay.total
             # stacked deltas [N, total] and W0 [total], plan layout, fp32, resident.  Already
             # packed tensors (e.g. received by NCCL broadcast) are taken as they are.
-            if isinstance(deltas, torch.Tensor):
+            self._zero_row: Optional[torch.Tensor] = None
+            if deltas is None:
+                self.deltas = None
+            elif isinstance(deltas, torch.Tensor):
                 if deltas.shape != (self.n_clients, total) or deltas.dtype != torch.float32:
                     raise ValueError(f"packed deltas must be fp32 [N, {total}]")
                 self.deltas = deltas.to(self.device).contiguous()
@@ -148,13 +158,23 @@ class CoalitionEngine:
         V, Mz = self.lay.vec_size, self.lay.mat_size
         w0v = self.w0[:V] if self.w0 is not None else None
         w0m = self.w0[V:] if self.w0 is not None else None
-        ops.aggregate(self.deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
-        ops.aggregate(self.deltas[:, V:], w0m, ratios, out=self.wmat, P=Mz)
+        deltas = self.deltas
+        if deltas is None:
+            # no single-round stack: only W_0 itself can be asked for (all-zero rows = no member).  K1 skips
+            # zero-ratio clients, so one zero placeholder row serves any N.
+            if bool((ratios != 0).any()):
+                raise ValueError("this engine holds no single-round deltas (deltas=None): use evaluate_rounds")
+            if self._zero_row is None:
+                self._zero_row = torch.zeros((1, self.lay.total), dtype=torch.float32, device=self.device)
+            deltas, ratios = self._zero_row, torch.zeros((Cn, 1), dtype=torch.float32)
+        ops.aggregate(deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
+        ops.aggregate(deltas[:, V:], w0m, ratios, out=self.wmat, P=Mz)
 
-    def _run_batch(self, ratio_rows: Sequence[Sequence[float]],
-                   image_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _run_batch(self, ratio_rows: Sequence[Sequence[float]], image_range: Optional[Tuple[int, int]] = None,
+                   records: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """One batch of <= coalition_batch coalitions given their dense ratio rows, scored on the validation
-        images [lo, hi) (default: all of them)."""
+        images [lo, hi) (default: all of them).  With ``records`` (int64 [Cn, 2] device view, e.g. a slice of the
+        all-gather send buffer) K5 writes the packed (correct, loss_sum) records there and nothing is returned."""
         Cn = len(ratio_rows)
         lay, cfg = self.lay, self.cfg
         # FedAvg ratios: fp64 on the host (as the reference computes them), rounded once to fp32;
@@ -174,6 +194,14 @@ class CoalitionEngine:
             b = min(self.image_chunk, hi - s)
             self.plan.forward(self.wvec[:Cn], self.wmat, self.patches, s * npch, b, logits, image_offset=s)
         self.kernel_launches += 2 + ((hi - lo + self.image_chunk - 1) // self.image_chunk) * (3 + 7 * cfg.layers) + 1
+        if records is not None:
+            if hi > lo:
+                ops.score_records(logits[:, lo:hi], self.labels[lo:hi], records)
+            else:
+                records.zero_()
+            if self.keep_logits:
+                self.last_logits = logits.clone()
+            return None, None
         if (lo, hi) == (0, self.n_val):
             correct, loss = ops.score(logits, self.labels)
         elif hi > lo:
@@ -210,9 +238,12 @@ class CoalitionEngine:
     def _run_batch_rounds(self, rows_per_round: Sequence[Sequence[Sequence[float]]]):
         """One batch of coalitions; ``rows_per_round[t][c]`` = dense FedAvg ratio row of coalition c in round t
         (all zeros when none of its members was selected in that round)."""
-        R, Cn = len(rows_per_round), len(rows_per_round[0])
-        if R != len(self.round_deltas) or R == 0:
+        R = len(rows_per_round)
+        if R != len(self.round_deltas):
             raise ValueError("one ratio table per round expected (set_round_deltas first)")
+        if R == 0:
+            raise ValueError("no rounds: use evaluate() with all-zero rows (the model is W_0)")
+        Cn = len(rows_per_round[0])
         lay, cfg = self.lay, self.cfg
         V, Mz = lay.vec_size, lay.mat_size
         if self._partial is None:   # fp32 partial models [coalition_batch, total], W_0 + the rounds so far
@@ -240,8 +271,13 @@ class CoalitionEngine:
             self.last_logits = logits.clone()
         return correct, loss
 
-    def evaluate_rounds(self, rows_per_round: Sequence[Sequence[Sequence[float]]]) -> Tuple[List[int], List[float]]:
-        """Like ``evaluate`` for models reconstructed from several FL rounds: ``rows_per_round[t][c]``."""
+    def evaluate_rounds(self, rows_per_round: Sequence[Sequence[Sequence[float]]],
+                        n_coalitions: Optional[int] = None) -> Tuple[List[int], List[float]]:
+        """Like ``evaluate`` for models reconstructed from several FL rounds: ``rows_per_round[t][c]``.
+        No round at all (``include_from_round > current_round`` in the reference's loop,
+        utils_fed_shapley.py:166-176): every model is W_0; ``n_coalitions`` says how many."""
+        if len(rows_per_round) == 0:
+            return self.evaluate([[0.0] * self.n_clients] * int(n_coalitions or 0))
         n = len(rows_per_round[0])
         correct: List[int] = []
         loss: List[float] = []
@@ -286,6 +322,14 @@ class CoalitionEngine:
                 correct += c.cpu().tolist()
                 loss += l.cpu().tolist()
         return correct, loss
+
+    def evaluate_into(self, ratio_rows: Sequence[Sequence[float]], records: torch.Tensor,
+                      image_range: Optional[Tuple[int, int]] = None) -> None:
+        """``evaluate`` without the host read-back: the packed per-coalition records land in ``records``
+        (int64 [len(ratio_rows), 2] on this device), asynchronously on the current stream."""
+        with torch.cuda.device(self.device):
+            for s in range(0, len(ratio_rows), self.coalition_batch):
+                self._run_batch(ratio_rows[s:s + self.coalition_batch], image_range, records=records[s:s + self.coalition_batch])
 
     def evaluate_state_dict(self, sd: Dict[str, torch.Tensor]) -> Tuple[int, float]:
         """Score one explicit model (the reference's plain ``evaluation(args, net, loader)``)."""

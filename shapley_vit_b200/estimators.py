@@ -43,6 +43,14 @@ def _prefetch(game, coalitions: Iterable[Iterable[int]]) -> None:
         batch([tuple(int(j) for j in c) for c in coalitions])
 
 
+def _shared_seed(seed: Optional[int]) -> Optional[int]:
+    """Under torch.distributed every rank must draw the same coalitions (dist.shared_seed); a single process keeps
+    the reference's behaviour (None = OS entropy, utils_shapley.py:253, 278)."""
+    from . import dist
+
+    return dist.shared_seed(seed)
+
+
 def _zero_vector(game) -> List[Dict[int, float]]:
     return [{cid: 0 for cid in range(game._n_all)} for _ in range(game.utility_dim)]
 
@@ -96,7 +104,7 @@ def shapley_monte_carlo(game, m: int, seed: Optional[int] = None):
     """m sampled permutations (cumulative ``RandomState.shuffle`` of the player list);
     phi_i = mean marginal contribution of i over the permutations."""
     n = game.n
-    rs = np.random.RandomState(seed)
+    rs = np.random.RandomState(_shared_seed(seed))
     order = list(game.selected_clients)
     perms: List[List[int]] = []
     for _ in range(m):
@@ -121,6 +129,7 @@ def shapley_monte_carlo(game, m: int, seed: Optional[int] = None):
 def _cc_draws(n: int, m: int, seed: Optional[int]):
     """The reference's draw sequence: one private-RandomState shuffle of arange(n) (cumulative)
     then one ``random.randint(1, n)`` from the GLOBAL python RNG per sample."""
+    seed = _shared_seed(seed)
     rs = np.random.RandomState(seed)
     if seed is not None:
         random.seed(seed)
@@ -200,10 +209,19 @@ def call_shapley_computation_method(args, game, logger=None):
 
         cls = {"gtg": compared.GTG, "mr": compared.MR, "tmr": compared.TMR, "group_testing": compared.Fed_SV}[method]
         shapley_value = []
+        seed = _shared_seed(seed)
         for dim in range(game.utility_dim):
             if seed is not None:
                 np.random.seed(seed)
-            sv = cls(dim).compute_shapley_value(game, 0)
+            if method == "group_testing":
+                # The class keeps the reference's conventions when used directly (1-based result keys and the
+                # ``S.count(i + 1)`` membership test, compared_methods.py:165, under which client 0 is never
+                # valued).  The reference's dispatcher has no group-testing branch, so this additive one uses the
+                # intended 0-based membership and re-keys the result: every client is valued, sum = v(N).
+                sv = compared.Fed_SV(dim, one_based_membership=False).compute_shapley_value(game, 0)
+                sv = {cid: sv[cid + 1] for cid in range(game._n_all)}
+            else:
+                sv = cls(dim).compute_shapley_value(game, 0)
             shapley_value.append({cid: sv.get(cid, 0) for cid in range(game._n_all)})
         print(f"{method}: {shapley_value}")
     else:

@@ -71,8 +71,7 @@ def compute_utilities_lazy(args, previous_utility, client_model_all_rounds, clie
             loader = fake_server.valid_loader
             val = loader if isinstance(loader, ValidationSet) else ValidationSet.from_loader(cfg, loader, precision, device)
             w0 = _clean_keys(_state_dict_of(init_global_model))
-            zero = [{k: v * 0 for k, v in w0.items()} for _ in range(n_all)]
-            engine = CoalitionEngine(cfg, w0, zero, val, precision=precision,
+            engine = CoalitionEngine(cfg, w0, None, val, precision=precision, n_clients=n_all,
                                      coalition_batch=a.get("coalition_batch", 8), image_chunk=a.get("image_chunk", 128),
                                      device=device)
         engine.set_round_deltas([[(_clean_keys(d) if d is not None else None) for d in client_model_all_rounds[t]]
@@ -84,6 +83,8 @@ def compute_utilities_lazy(args, previous_utility, client_model_all_rounds, clie
 
     def evaluate(flat_rows):
         # dist.sharded_evaluate shards a flat list of rows; a row here is the per-round stack of one subset
+        if not rounds:      # no round included: every subset's model is W_0 (the reference then scores W_0 2^N - 1 times)
+            return evaluator.evaluate_rounds([], n_coalitions=len(flat_rows))
         return evaluator.evaluate_rounds([[fr[t] for fr in flat_rows] for t in range(len(rounds))])
 
     per_subset = [[rows_per_round[t][i] for t in range(len(rounds))] for i in range(len(subsets))]

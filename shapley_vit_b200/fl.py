@@ -82,17 +82,28 @@ def get_aggregated_model(nets: Sequence[Dict[str, torch.Tensor]], ratio: Sequenc
 
 
 class _EvalCache:
-    """Validation sets already resident on the device, keyed by the loader object."""
-    sets: Dict[tuple, ValidationSet] = {}
+    """Validation sets already resident on the device, keyed by the loader object.  The entry holds the loader
+    itself (so its id cannot be recycled by another object while the entry lives) and the cache is bounded:
+    the least recently used set is dropped, which frees its images in HBM."""
+    MAX_SETS = 4
+    sets: "OrderedDict[tuple, tuple]" = OrderedDict()
 
     @classmethod
     def get(cls, loader, cfg, precision: int, device) -> ValidationSet:
         key = (id(loader), precision, str(device), cfg)
-        vs = cls.sets.get(key)
-        if vs is None:
-            vs = ValidationSet.from_loader(cfg, loader, precision, device)
-            cls.sets[key] = vs
+        hit = cls.sets.get(key)
+        if hit is not None and hit[0] is loader:
+            cls.sets.move_to_end(key)
+            return hit[1]
+        vs = ValidationSet.from_loader(cfg, loader, precision, device)
+        cls.sets[key] = (loader, vs)
+        while len(cls.sets) > cls.MAX_SETS:
+            cls.sets.popitem(last=False)
         return vs
+
+    @classmethod
+    def clear(cls) -> None:
+        cls.sets.clear()
 
 
 def evaluation(args, net, eval_loader):

@@ -117,7 +117,8 @@ class Game:
             n_val = self._n_val()
             # fewer pending coalitions than ranks: split the validation set instead (if the evaluator can)
             can_split = self._evaluator is None or getattr(self._evaluator, "supports_image_range", False)
-            correct, loss_sum = dist.sharded_evaluate(ev.evaluate, rows, n_val if can_split else 0)
+            correct, loss_sum = dist.sharded_evaluate(ev.evaluate, rows, n_val if can_split else 0,
+                                                      evaluate_into=getattr(ev, "evaluate_into", None))
             for k, c, l in zip(row_keys, correct, loss_sum):
                 if math.isnan(l):
                     raise ValueError("loss is nan")

@@ -190,6 +190,22 @@ def score(logits: torch.Tensor, labels: torch.Tensor, correct: Optional[torch.Te
     return (correct, loss_sum, pred) if want_pred else (correct, loss_sum)
 
 
+def score_records(logits: torch.Tensor, labels: torch.Tensor, records: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+    """K5 into packed records: ``records`` is an int64 [C, 2] device tensor (a slice of the all-gather send buffer);
+    row c receives (correct, bit pattern of the fp64 loss_sum) -- the 16-byte svit_record of include/svit.h."""
+    _cuda(logits, "logits", torch.float32)
+    _cuda(labels, "labels", torch.int64)
+    _cuda(records, "records", torch.int64)
+    if logits.dim() != 3 or not logits[0].is_contiguous():
+        raise ValueError("logits must be [C, n, n_cls] with contiguous [n, n_cls] slabs")
+    Cn, n, n_cls = logits.shape
+    if records.shape != (Cn, 2) or not records.is_contiguous():
+        raise ValueError("records must be a contiguous int64 [C, 2] tensor")
+    check(_lib.load().svit_score_records(_ptr(logits), logits.stride(0) if Cn > 1 else n * n_cls, _ptr(labels.contiguous()), Cn, n,
+                                         n_cls, _ptr(records), int(accumulate), _stream(logits)))
+    return records
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               out_dtype: torch.dtype = torch.float32, fmt: int = FMT_PLAIN):
     """x [G, rows, h] fp32, gamma/beta [G, h] fp32 -> y [G, rows, h] (a tensor, or an OperandArray for a split fmt)."""

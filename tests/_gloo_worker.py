@@ -35,7 +35,20 @@ def main():
     game2._evaluator = OracleEvaluator(cfg, w0, deltas, images, labels)
     u_single = game2.eval_utility((0, 2))
     split = dict(utility=u_single, counts=list(game2.counts[frozenset((0, 2))]), ranges=game2._evaluator.ranges)
-    res = dict(rank=rank, world=ws, evaluated_here=sum(game._evaluator.calls), split=split,
+    # stochastic estimators under world_size > 1: seed None must still give every rank the same draws
+    # (dist.shared_seed: one entropy draw of rank 0, broadcast), an explicit seed the single-process result
+    def fresh():
+        g = Game(clients, ServerBase({}, w0, clients, None, None, None), w0, deltas, [True] * 3, prev, 2, {})
+        g._evaluator = OracleEvaluator(cfg, w0, deltas, images, labels)
+        return g
+
+    as_lists = lambda phi: [[phi[d][c] for c in range(3)] for d in range(2)]
+    g_cc, g_mc, g_cc5 = fresh(), fresh(), fresh()
+    stochastic = dict(cc_none=as_lists(estimators.shapley_comp_contrib(g_cc, 4, seed=None)),
+                      mc_none=as_lists(estimators.shapley_monte_carlo(g_mc, 2, seed=None)),
+                      cc_seed5=as_lists(estimators.shapley_comp_contrib(g_cc5, 4, seed=5)),
+                      cc_none_keys=sorted(",".join(map(str, sorted(k))) for k in g_cc.counts))
+    res = dict(rank=rank, world=ws, stochastic=stochastic, evaluated_here=sum(game._evaluator.calls), split=split,
                counts={",".join(map(str, sorted(k))): v for k, v in game.counts.items()},
                sv=[[sv[d][c] for c in range(3)] for d in range(2)],
                bounds=[dist.shard_bounds(7, r, ws) for r in range(ws)])

@@ -59,6 +59,21 @@ def test_two_rank_gloo_matches_single_process(tmp_path):
     assert ranks[0]["split"] == ranks[1]["split"] or ranks[0]["split"]["counts"] == ranks[1]["split"]["counts"]
 
 
+    # stochastic estimators: with seed None the ranks still drew the same coalitions (shared seed) and agree;
+    # with an explicit seed the two-rank result is the single-process one
+    assert ranks[0]["stochastic"] == ranks[1]["stochastic"]
+    assert ranks[0]["stochastic"]["cc_seed5"] == single["stochastic"]["cc_seed5"]
+
+
+def test_rows_digest_detects_divergent_lists():
+    from shapley_vit_b200.dist import _rows_digest
+
+    a = [[0.5, 0.5, 0.0], [0.0, 1.0, 0.0]]
+    assert _rows_digest(a) == _rows_digest([list(r) for r in a])
+    assert _rows_digest(a) != _rows_digest(a[::-1])
+    assert 0 <= _rows_digest(a) < 2 ** 63
+
+
 def test_shard_bounds_cover_everything():
     from shapley_vit_b200.dist import shard_bounds
 

@@ -137,3 +137,26 @@ def test_dispatcher_default_is_comp_contrib(capsys):
     assert "Comp contrib" in capsys.readouterr().out
     with pytest.raises(ValueError):
         estimators.call_shapley_computation_method({"approximation_method": "nope"}, g, None)
+
+
+def test_dispatcher_group_testing_values_every_client(capsys):
+    """The additive 'group_testing' branch: 0-based membership and keys, so client 0 is valued and the vector sums
+    to v(N) (the class used directly keeps the reference's 1-based conventions, compared_methods.py:165)."""
+    g = TableGame(5, {tuple(k): v for k, v in toy_table(5, 11).items()})
+    sv = estimators.call_shapley_computation_method({"approximation_method": "group_testing", "seed": 2}, g, None)
+    vN = g.eval_utility(range(5))
+    for dim in range(2):
+        assert sorted(sv[dim]) == list(range(5))
+        assert sum(sv[dim].values()) == pytest.approx(vN[dim], abs=1e-6)
+        assert sv[dim][0] != 0
+        # (a 200-sample group test is a noisy estimator; only its constraints are asserted)
+    assert "group_testing" in capsys.readouterr().out
+
+
+def test_fed_sv_solve_feasible_respects_the_constraints():
+    rng = np.random.RandomState(0)
+    x_true = rng.uniform(-0.2, 0.4, size=6)
+    UD = np.subtract.outer(x_true, x_true).astype(np.float32)
+    x = compared.Fed_SV(0).solveFeasible(6, float(x_true.sum()), UD)
+    assert sum(x) == pytest.approx(float(x_true.sum()), abs=1e-6)
+    assert np.allclose(x, x_true, atol=1e-5)

@@ -94,3 +94,26 @@ def test_server_ratio_hook_is_used():
     game.eval_utility([0, 1])
     assert seen == [2]
     assert game.server.get_agg_ratio(selected_clients=game.clients[:2]) == [1000 / 3000, 2000 / 3000]
+
+
+def test_eval_cache_holds_the_loader_and_is_bounded(monkeypatch):
+    """the cache key is id(loader); the entry must keep the loader alive (no id reuse) and evict."""
+    from shapley_vit_b200 import fl
+
+    made = []
+
+    class FakeVS:
+        def __init__(self, tag):
+            self.tag = tag
+
+    monkeypatch.setattr(fl.ValidationSet, "from_loader", staticmethod(lambda cfg, loader, p, d: made.append(loader) or FakeVS(len(made))))
+    fl._EvalCache.clear()
+    loaders = [object() for _ in range(6)]
+    first = fl._EvalCache.get(loaders[0], "cfg", 0, "cuda:0")
+    assert fl._EvalCache.get(loaders[0], "cfg", 0, "cuda:0") is first and len(made) == 1
+    for ld in loaders[1:]:
+        fl._EvalCache.get(ld, "cfg", 0, "cuda:0")
+    assert len(fl._EvalCache.sets) == fl._EvalCache.MAX_SETS
+    assert all(entry[0] in loaders for entry in fl._EvalCache.sets.values())      # loaders are referenced
+    assert fl._EvalCache.get(loaders[0], "cfg", 0, "cuda:0") is not first            # evicted, rebuilt
+    fl._EvalCache.clear()

@@ -112,3 +112,26 @@ def test_gpu_multi_round_models_bit_exact_and_utilities():
                                              engine=eng)
             assert max(abs(a - b) for a, b in zip(util[0], case["acc"])) <= tol_acc + 1e-12
             assert max(abs(a - b) for a, b in zip(util[1], case["loss"])) <= tol_loss
+
+
+def test_no_round_included_scores_w0_for_every_subset():
+    """include_from_round > current_round: the reference's loop (utils_fed_shapley.py:166-176) adds no round, so
+    every subset's model is W_0 and every utility is evaluation(W_0) - previous_utility = 0."""
+    from shapley_vit_b200.fed_shapley import compute_utilities_lazy
+
+    meta, cfg, w0, round_deltas, selection, n_train, images, labels = _inputs()
+    clients = [ClientBase(i, {}, None, synth.SizedStub(n)) for i, n in enumerate(n_train)]
+    server = ServerBase({}, None, clients, None, None, None)
+    subsets = powerset(range(len(n_train)))
+
+    class W0Only(OracleRoundsEvaluator):
+        def evaluate_rounds(self, rows_per_round, n_coalitions=None):
+            assert rows_per_round == []
+            _, _, det = restate.evaluation(self.w0, self.cfg, self.images, self.labels, return_details=True)
+            return [int(det["correct"])] * n_coalitions, [float(det["loss_sum"])] * n_coalitions
+
+    ev = W0Only(cfg, w0, [], images, labels)
+    util, _ = compute_utilities_lazy({"num_clients": len(n_train)}, meta["previous_utility"], round_deltas, selection, server,
+                                     clients, None, subsets, 2, 0, 1, evaluator=ev)
+    assert list(util[0]) == pytest.approx([0.0] * len(subsets), abs=1e-12)
+    assert list(util[1]) == pytest.approx([0.0] * len(subsets), abs=2e-6)
