@@ -55,6 +55,10 @@ def parse_args():
     ap.add_argument("--cpu-sample-images", type=int, default=256)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-throughput-mode", action="store_true")
+    ap.add_argument("--time-to-shapley", action="store_true",
+                    help="also time the WHOLE exact-Shapley job (all 2^N - 1 coalitions, strong scaling over the ranks); "
+                         "on by default when --gpus >= 4 (at 1-2 GPUs it adds minutes)")
+    ap.add_argument("--no-time-to-shapley", action="store_true")
     ap.add_argument("--parity-clients", type=int, default=4)
     ap.add_argument("--parity-images", type=int, default=10000)
     return ap.parse_args()
@@ -356,6 +360,65 @@ def parity_leg(a, cfg, lay, deltas, w0, images_host, labels_host, dev, val_main=
 
 
 # ----------------------------------------------------------------------------------------------
+def time_to_shapley(a, eng, deltas, w0, clients, server, coalitions, dev, rank, ws, per_gpu_rate):
+    """Strong scaling: wall-clock seconds from "rank 0 holds the client weights" to "every rank holds the exact
+    Shapley vector" for the WHOLE game of the workload (BASELINE config 2: all 255 coalitions over the 10 000 images):
+    NCCL broadcast of the stacked deltas + W0, the coalition slices, ONE all-gather of the packed per-coalition records
+    (written by K5 straight into the send buffer), the fp64 accumulation on every rank.  Max over ranks.
+    Then rank 0 recomputes a sample of coalitions that OTHER ranks owned and checks the gathered records bit for bit."""
+    import torch
+
+    from shapley_vit_b200 import dist
+    from shapley_vit_b200.estimators import shapley_exact
+    from shapley_vit_b200.game import Game
+
+    N = a.clients
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    t0 = time.perf_counter()
+    dist.broadcast_(deltas)                       # eng.deltas / eng.w0 are these tensors: received in place
+    dist.broadcast_(w0)
+    torch.cuda.synchronize(dev)
+    t_bcast = time.perf_counter() - t0
+    game = Game(clients, server, None, [None] * N, [True] * N, [0.0, 0.0], 2, {"precision": a.precision})
+    game._engine = eng
+    phi = shapley_exact(game)                     # plan -> eval_utilities (sharded, one all-gather) -> accumulation
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    if ws > 1:
+        import torch.distributed as td
+
+        t = torch.tensor([wall, t_bcast], dtype=torch.float64, device=dev)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        wall, t_bcast = float(t[0]), float(t[1])
+    out = None
+    if rank == 0:
+        n = len(coalitions)
+        ideal = n / ws / per_gpu_rate
+        out = {"value": wall, "unit": "s", "coalitions": n, "n_gpus": ws, "scaling": "strong",
+               "broadcast_s": t_bcast, "broadcast_bytes": int(deltas.numel() * 4 + w0.numel() * 4),
+               "ideal_s": ideal, "vs_ideal": wall / ideal,
+               "ideal": "coalitions / n_gpus / (this line's per-GPU rate with everything resident)",
+               "shapley_acc": [phi[0][c] for c in range(N)],
+               "collectives": "2 broadcasts (client weights, once) + 1 all-gather of 16-byte records"}
+        if ws > 1:                                 # cross-rank identity on hardware: recompute what others computed
+            keys = list(coalitions)
+            picks = []
+            for r in range(1, ws):
+                lo, hi = dist.shard_bounds(n, r, ws)
+                if hi > lo:
+                    picks.append(lo + (hi - lo) // 2)
+            picks = picks[:4]
+            rows = [game._ratio_row(frozenset(keys[i])) for i in picks]
+            c, l = eng.evaluate(rows)
+            same = all((int(ci), float(li)) == game.counts[frozenset(keys[i])] for i, ci, li in zip(picks, c, l))
+            out["cross_rank_identity"] = {"coalitions_recomputed_on_rank0": [list(keys[i]) for i in picks],
+                                          "bit_identical": bool(same)}
+    dist.barrier()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 def run_ours(a):
     import torch
 
@@ -522,6 +585,14 @@ def run_ours(a):
                        "the upload of step i+1 overlaps the compute of step i, the first upload is not overlapped), ratio rows H2D, "
                        "per-coalition (correct, loss_sum) D2H through Game.eval_utilities; client deltas/W0 stay resident"}
 
+    # ---- strong scaling: the whole job, "time to the Shapley vector" ---------------------------------
+    tts = None
+    if (a.time_to_shapley or ws >= 4) and not a.no_time_to_shapley:
+        tts = time_to_shapley(a, eng, deltas, w0, clients, server, coalitions, dev, rank, ws, value / ws)
+    elif rank == 0:
+        tts = {"value": None, "note": f"not run at {ws} GPU(s) by default ({len(coalitions)} coalitions / {value:.2f} evals/s = "
+                                      f"{len(coalitions) / value:.0f} s): pass --time-to-shapley; runs by default from 4 GPUs"}
+
     if rank != 0:
         if ws > 1:
             td.destroy_process_group()
@@ -616,6 +687,7 @@ def run_ours(a):
                    "hf_equivalent_tflops_per_s_per_gpu": model_flops_nominal / (elapsed_ms / 1e3) / 1e12},
         "roofline": roofline, "roofline_aggregate": roofline_agg, "breakdown": breakdown,
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "throughput_mode": throughput_mode,
+        "time_to_shapley_s": tts["value"] if tts else None, "time_to_shapley": tts,
     }
     if ws == 1 and not a.no_cpu_baseline:
         try:

@@ -146,6 +146,13 @@ __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// L2 prefetch of one box (no shared-memory destination): issued kPrefetchAhead k-blocks ahead of the ring, so that the
+// operand stream that comes from DRAM (A: the activations of the previous kernel, read once) is an L2 hit by the time
+// its stage is requested -- the ring alone (4-5 stages x 512 tensor cycles) is shorter than a loaded DRAM round trip
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // arrive (once the MMAs issued so far complete) on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -249,6 +256,7 @@ struct TcShape {
   int mode;       // svit_operand_format of the operands: the schedule of the K loop
   int nk_main;    // k-blocks of one fp16 / tf32 pass (128 bytes of K each)
   int nk_aux;     // C8: k-blocks (128 e4m3 values of K) of one compensation pass
+  int prefetch_ahead;  // pair kernel: A k-blocks prefetched into L2 beyond the smem ring (0 = off)
 };
 
 // the operand planes (main, aux1, aux2) of A and of B; unused entries repeat the main plane
@@ -835,12 +843,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's full barriers
     int s = 0;
     uint32_t ph = 0;
+    // look-ahead cursor of the L2 prefetch: (tile, k-block) kPrefetchAhead steps past the load cursor
+    int64_t pf_tile = pair;
+    int pf_kb = 0, pf_g = 0, pf_m0 = 0;
+    auto pf_decode = [&]() {
+      pf_g = (int)(pf_tile / tiles_per_group);
+      pf_m0 = (int)((pf_tile % tiles_per_group) / sh.tiles_n) * (2 * BM) + (int)rank * BM;
+    };
+    auto pf_step = [&]() {  // prefetch this CTA's A box of the cursor's k-block, advance the cursor
+      if (pf_tile >= sh.total_tiles) return;
+      if (elect_one()) {
+        int ia, ib, kc;
+        kstep<KIND>(sh, pf_kb, ia, ib, kc);
+        tma_prefetch_3d(&maps.a[ia], kc, pf_m0, sh.a_grouped ? pf_g : 0);
+      }
+      __syncwarp();
+      if (++pf_kb == sh.num_kb) {
+        pf_kb = 0, pf_tile += npairs;
+        if (pf_tile < sh.total_tiles) pf_decode();
+      }
+    };
+    const int ahead = sh.prefetch_ahead;
+    if (ahead > 0 && pf_tile < sh.total_tiles) {
+      pf_decode();
+      for (int i = 0; i < ahead + C::STAGES; ++i) pf_step();
+    }
     for (int64_t tile = pair; tile < sh.total_tiles; tile += npairs) {
       const int g = (int)(tile / tiles_per_group);
       const int rem = (int)(tile % tiles_per_group);
       const int m0 = (rem / sh.tiles_n) * (2 * BM) + (int)rank * BM;
       const int n0 = (rem % sh.tiles_n) * BN + (int)rank * (BN / 2);
       for (int kb = 0; kb < sh.num_kb; ++kb) {
+        if (ahead > 0) pf_step();
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
@@ -1053,6 +1087,8 @@ int gemm_tc(int precision, const Operand& A, int64_t a_off, int64_t a_gs, const 
   sh.nk_aux = mode == SVIT_FMT_C8 ? (K + 127) / 128 : 0;
   sh.num_kb = mode == SVIT_FMT_X3 ? 3 * sh.nk_main : sh.nk_main + 2 * sh.nk_aux;
   sh.a_grouped = a_gs ? 1 : 0;
+  static const int pf_env = [] { const char* e = getenv("SVIT_GEMM_PREFETCH"); return e ? atoi(e) : -1; }();
+  sh.prefetch_ahead = pf_env >= 0 ? pf_env : 8;
   SVIT_CHECK_ARG(b_gs != 0 || G == 1, "gemm_tc: B must be grouped when G > 1");
   // instruction descriptor: D fp32, A/B format, both K-major, N, M (format 0 is fp16 for kind::f16 and e4m3 for
   // kind::f8f6f4: the compensation passes of F16C8 use the same descriptor)

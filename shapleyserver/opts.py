@@ -80,6 +80,10 @@ _NEW_FLAGS = [
                                                "reference's start.py:274-276 (there: 16); 0: plain ViT")),
     (("--lora-alpha", "--lora_alpha"), dict(type=float, default=8.0, help="LoRA alpha (reference: 8)")),
     (("--synthetic",), dict(action=_STORE_TRUE, default=False, help="synthetic validation set and client models")),
+    (("--synthetic-data", "--synthetic_data"), dict(action=_STORE_TRUE, default=False,
+        help="synthetic validation set only: the client models come from the reference's checkpoint layout "
+             "(shapleyserver/local_training/client_<i>_model/ViT_epoch_9.pth.tar under the working directory), the initial "
+             "global model from -loadModel")),
     (("--val-size", "--val_size"), dict(type=int, default=1000, help="synthetic validation images")),
 ]
 

@@ -11,7 +11,8 @@ Deliberate differences from the reference: the models are
 objects (the reference binds four names to one module, so every delta is zero), the number of
 clients is not pinned to 3, the estimator's result is kept (``LAST_SHAPLEY_VALUE`` and the return
 value of ``start()``) instead of only printed, and ``--synthetic`` replaces the private OCT data
-and the pretrained HF checkpoint, neither of which ships with the reference.
+and the pretrained HF checkpoint, neither of which ships with the reference (``--synthetic_data`` replaces the
+data only: the client models are then read from the reference's checkpoint files, waiting for each to appear).
 """
 from __future__ import annotations
 
@@ -132,7 +133,7 @@ def getOCTData2():
     synthetic dict-sample dataset of the same contract takes its place."""
     from shapley_vit_b200 import layout, synth
 
-    if not opt.synthetic:
+    if not (opt.synthetic or opt.synthetic_data):
         try:
             from .datasets.dataloader_cell import XrayDataLoader as CellDataLoader  # user-provided
 

@@ -106,3 +106,58 @@ def test_lora_container_takes_peft_checkpoints():
     fresh = LoraViTForImageClassification(cfg, r=4)
     fm = lora.merged_state_dict(fresh.state_dict(), 8.0)
     assert torch.equal(fm[q + ".weight"], fresh.state_dict()[f"base_model.model.{q}.base_layer.weight"])
+
+
+@pytest.mark.gpu
+def test_main_shapley_reads_client_checkpoints_and_waits_for_a_late_one(tmp_path):
+    """N3 (reference start.py:134-151, 198-222): without --synthetic the client models are read from
+    ``<cwd>/shapleyserver/local_training/client_<i>_model/ViT_epoch_9.pth.tar`` -- ``{'state_dict': ...}`` files whose
+    keys carry DataParallel's ``module.`` prefix -- and a checkpoint that is not there yet (its writer has not released
+    it) is waited for.  Only the validation data is synthetic."""
+    import threading
+
+    cfg = layout.vit_preset("tiny", image=32, n_cls=10)
+    w0 = synth.make_state_dict(cfg, 3)
+    client_sds = [synth.make_client_state_dict(w0, j, 3) for j in range(3)]
+    init_path = tmp_path / "init_global.pth.tar"
+    torch.save({"state_dict": w0, "epoch": 0}, init_path)
+    finals = []
+    for j, sd in enumerate(client_sds):
+        d = tmp_path / "shapleyserver" / "local_training" / f"client_{j + 1}_model"
+        d.mkdir(parents=True)
+        final = d / "ViT_epoch_9.pth.tar"
+        target = final if j < 2 else d / "ViT_epoch_9.pth.tar.writing"      # the third one is still being written
+        torch.save({"state_dict": {f"module.{k}": v for k, v in sd.items()}, "epoch": 9}, target)
+        finals.append((target, final))
+    release = threading.Timer(4.0, lambda: os.replace(*finals[2]))
+    release.start()
+    flags = ["--synthetic_data", "--vit_size", "tiny", "--image_size", "32", "--num_classes", "10", "--val_size", "96",
+             "--num_clients", "3", "--dtype", "f32", "--seed", "3", "--approximation_method", "exact",
+             "-loadModel", str(init_path), "--exp_dir", str(tmp_path)]
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "mainShapley.py"), *flags], capture_output=True, text=True,
+                             cwd=str(tmp_path), timeout=600)
+    finally:
+        release.cancel()
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("Waiting for the file to be unlocked...") >= 1
+    assert out.stdout.count("Model loaded!") == 3
+    sv = ast.literal_eval(re.search(r"^Exact: (.*)$", out.stdout, re.M).group(1))
+    deltas = [restate.get_difference_between_network_weights(sd, w0) for sd in client_sds]
+    images, labels = synth.make_val_set(cfg, 96, 3)
+    # the reference hands every client the validation dataset as its "training set" (start.py:163-170): equal sizes
+    want = oracle_exact(w0, deltas, cfg, images, labels, [96, 96, 96])
+    for d in range(2):
+        assert [sv[d][c] for c in range(3)] == pytest.approx(want[d], abs=1e-5 if d else 1e-12)
+
+
+def test_check_local_training_model_exist_waits(tmp_path, capsys):
+    """CPU: the wait-for-unlock loop (reference start.py:198-222) returns once the file has appeared."""
+    import threading
+
+    from shapleyserver.start import checkLocalTrainingModelExist
+
+    path = tmp_path / "ViT_epoch_9.pth.tar"
+    threading.Timer(0.3, lambda: path.write_bytes(b"x")).start()
+    assert checkLocalTrainingModelExist(str(path), poll_seconds=0.05) is True
+    assert "Waiting for the file to be unlocked..." in capsys.readouterr().out

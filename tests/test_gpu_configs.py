@@ -84,3 +84,34 @@ def test_cfg4_vit_large_batches_of_32_models(prec, tol):
         worst = max(worst, (logits[ci] - want).abs().max().item())
     print(f"[{prec}] ViT-L, 32 models per group: max |dlogit| = {worst:.3e}")
     assert worst < tol
+
+
+def test_group_testing_on_the_engine_matches_the_oracle_driven_run():
+    """Fed_SV (group testing, compared_methods.py:121-243 with the SciPy LP for the Wolfram solve) through the CUDA engine:
+    same global-RNG draw sequence, same sampled coalitions, the same difference matrix UD (integer counts -> identical
+    accuracy utilities) and the same feasible point as the oracle-driven run.  5 clients, fp32 mode."""
+    gpu, ora = _games(5, 64, "f32")
+    res = []
+    for game in (gpu, ora):
+        np.random.seed(11)
+        fed = compared.Fed_SV(utility_index=0)
+        fed.CONVERGE_MIN_K = 40                      # 40 samples instead of 200: a parity case, not an estimate
+        sv = fed.compute_shapley_value(game, 0)
+        res.append((sv, fed.UD.copy(), fed.iterations, sorted(fed.Ut[0])))
+    (sv_g, ud_g, it_g, keys_g), (sv_o, ud_o, it_o, keys_o) = res
+    assert it_g == it_o and keys_g == keys_o
+    assert np.array_equal(ud_g, ud_o)
+    assert [sv_g[c + 1] for c in range(5)] == pytest.approx([sv_o[c + 1] for c in range(5)], abs=1e-9)
+    assert sum(sv_g.values()) == pytest.approx(gpu.eval_utility(range(5))[0], abs=1e-9)
+
+
+def test_cfg3_default_precision_keeps_the_monte_carlo_vector():
+    """The same 16-client Monte-Carlo run in the default precision (f16c8): utilities within one sample of the oracle's,
+    Shapley vector within north_star's 1e-3."""
+    gpu, ora = _games(16, 64, "f16c8")
+    sv = [estimators.shapley_monte_carlo(game, m=4, seed=9) for game in (gpu, ora)]
+    for d in range(2):
+        got, want = [sv[0][d][c] for c in range(16)], [sv[1][d][c] for c in range(16)]
+        assert max(abs(x - y) for x, y in zip(got, want)) < 1e-3
+    common = set(gpu.counts) & set(ora.counts)
+    assert all(abs(gpu.counts[k][0] - ora.counts[k][0]) <= 1 for k in common)
