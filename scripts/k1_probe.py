@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""One K1 shape, timed: python scripts/k1_probe.py N C [f16|f32] [P]   (for ncu: -k regex:aggregate)"""
+"""One K1 shape, timed: python scripts/k1_probe.py N C [f16|f32|c8|x3] [P]   (for ncu: -k regex:aggregate)"""
 import os
 import sys
 
@@ -19,7 +19,14 @@ masks = torch.rand(Cn, N) < 0.5
 masks[:, 0] |= ~masks.any(dim=1)
 n = torch.arange(1, N + 1, dtype=torch.float64) * 1000
 ratios = (masks * n / (masks * n).sum(dim=1, keepdim=True)).float()
-out = torch.empty(Cn, stride, dtype=dt, device="cuda")
+kind = sys.argv[3] if len(sys.argv) > 3 else "f16"
+if kind in ("c8", "x3"):
+    from shapley_vit_b200 import _lib
+    out = ops.OperandArray((Cn, stride), torch.float16, _lib.FMT_C8 if kind == "c8" else _lib.FMT_X3, "cuda")
+    out_es = 4
+else:
+    out = torch.empty(Cn, stride, dtype=dt, device="cuda")
+    out_es = out.element_size()
 fn = lambda: ops.aggregate(deltas, w0, ratios, out=out, P=P)
 fn()
 torch.cuda.synchronize()
@@ -30,5 +37,5 @@ for _ in range(4):
 b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 4
-by = 4.0 * P * (N + 1) + out.element_size() * P * Cn
-print(f"K1 N={N} C={Cn} {dt} P={P}: {ms*1e3:.1f} us  {by/ms/1e6:.0f} GB/s  ({by/ms/1e6/6555.5:.2f} of copy peak)")
+by = 4.0 * P * (N + 1) + out_es * P * Cn
+print(f"K1 N={N} C={Cn} {kind} P={P}: {ms*1e3:.1f} us  {by/ms/1e6:.0f} GB/s  ({by/ms/1e6/6555.5:.2f} of copy peak)")

@@ -348,11 +348,12 @@ __global__ void __launch_bounds__(kWarps3 * 32) attention_split_kernel(const Ope
 }
 
 // ---- the [CLS] query alone (last encoder layer): one warp per (sequence, head), fp32 CUDA-core arithmetic on
-// the reconstructed hi + lo values; ctx_cls [n_seq, h] in the consumer GEMM's split format
+// the reconstructed hi + lo values; ctx_cls [n_seq, h] in the consumer GEMM's split format.
+// HBM-bound (every key and value row of the head is read once: 4 * T * 64 * 2 bytes per item): a quarter-warp
+// covers one 128-byte row of a plane with 16-byte loads, four keys per warp iteration.
 template <int OFMT>
 __global__ void __launch_bounds__(256) attention_cls_split_kernel(const Operand qkv, const Operand ctx, int Tn, int heads,
                                                                   int64_t n_items) {
-  __shared__ float q_s[8][kD];
   __shared__ float p_s[8][256];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t item = blockIdx.x * 8LL + w;
@@ -360,45 +361,73 @@ __global__ void __launch_bounds__(256) attention_cls_split_kernel(const Operand 
   const int64_t seq = item / heads;
   const int head = (int)(item % heads);
   const int h = heads * kD;
-  const int64_t base = seq * (int64_t)Tn * 3 * h + head * kD;
-  for (int d = lane; d < kD; d += 32) q_s[w][d] = load_x3(qkv, base + d);
-  __syncwarp();
-  constexpr int KPL = 8;  // keys per lane: T <= 256
-  float s[KPL];
-  float m = -INFINITY;
+  const int g = lane >> 3, cb = lane & 7;  // key slot of the iteration, block of 8 channels
+  const __half* hi = static_cast<const __half*>(qkv.base);
+  const __half* lo = reinterpret_cast<const __half*>(qkv.aux1());
+  const int64_t base = seq * (int64_t)Tn * 3 * h + head * kD + cb * 8;
+  // 8 channels of one row, hi + lo -> fp32 (exact: 22 bits)
+  auto load8 = [&](int64_t idx, float (&v)[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(hi + idx));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(lo + idx));
+    const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, bl[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-  for (int k = 0; k < KPL; ++k) {
-    const int j = lane + k * 32;
-    s[k] = -INFINITY;
-    if (j < Tn) {
-      const int64_t kb = base + (int64_t)j * 3 * h + h;
-      float dot = 0.f;
-#pragma unroll 8
-      for (int d = 0; d < kD; ++d) dot = fmaf(q_s[w][d], load_x3(qkv, kb + d), dot);
-      s[k] = dot * 0.125f;
-      m = fmaxf(m, s[k]);
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack_f16x2(ah[i]), y = unpack_f16x2(bl[i]);
+      v[2 * i] = x.x + y.x, v[2 * i + 1] = x.y + y.y;
     }
+  };
+  float q[8];
+  load8(base, q);  // token 0 = [CLS]
+  for (int j0 = 0; j0 < Tn; j0 += 4) {
+    const int j = j0 + g;
+    float dot = 0.f;
+    if (j < Tn) {
+      float k[8];
+      load8(base + (int64_t)j * 3 * h + h, k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(q[i], k[i], dot);
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    if (cb == 0 && j < Tn) p_s[w][j] = dot * 0.125f;
   }
+  __syncwarp();
+  float m = -INFINITY;
+  for (int j = lane; j < Tn; j += 32) m = fmaxf(m, p_s[w][j]);
   m = warp_max(m);
   float sum = 0.f;
-#pragma unroll
-  for (int k = 0; k < KPL; ++k) {
-    s[k] = lane + k * 32 < Tn ? expf(s[k] - m) : 0.f;
-    sum += s[k];
+  for (int j = lane; j < Tn; j += 32) {
+    const float e = expf(p_s[w][j] - m);
+    p_s[w][j] = e;
+    sum += e;
   }
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
-#pragma unroll
-  for (int k = 0; k < KPL; ++k) p_s[w][lane + k * 32] = s[k] * inv;
   __syncwarp();
-  float o0 = 0.f, o1 = 0.f;  // the lane owns two consecutive channels
-  const int64_t vb = base + 2 * h + lane * 2;
-  for (int j = 0; j < Tn; ++j) {
-    const float pj = p_s[w][j];
-    o0 = fmaf(pj, load_x3(qkv, vb + (int64_t)j * 3 * h), o0);
-    o1 = fmaf(pj, load_x3(qkv, vb + (int64_t)j * 3 * h + 1), o1);
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  for (int j0 = 0; j0 < Tn; j0 += 4) {
+    const int j = j0 + g;
+    if (j < Tn) {
+      float v[8];
+      load8(base + (int64_t)j * 3 * h + 2 * h, v);
+      const float pj = p_s[w][j] * inv;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(pj, v[i], o[i]);
+    }
   }
-  store2_planes<OFMT>(ctx, seq * (int64_t)h + head * kD + lane * 2, o0, o1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // the four key slots
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+  }
+  if (g == 0) {
+    const int64_t oi = seq * (int64_t)h + head * kD + cb * 8;
+    store4_planes<OFMT>(ctx, oi, o[0], o[1], o[2], o[3]);
+    store4_planes<OFMT>(ctx, oi + 4, o[4], o[5], o[6], o[7]);
+  }
 }
 
 template <int KT, int OFMT>

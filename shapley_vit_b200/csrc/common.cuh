@@ -130,10 +130,15 @@ __device__ __forceinline__ void split_x3(float v0, float v1, uint32_t& hi, uint3
   const float2 h = unpack_f16x2(hi);
   lo = pack_f16x2_sat(__fsub_rn(v0, h.x), __fsub_rn(v1, h.y));
 }
+// C8 planes of two values: hi = fp16(x), hi8 = e4m3(4 hi), lo8 = e4m3(8192 (x - hi)).  hi8 is formed in fp16
+// arithmetic straight from the packed hi (4 hi is exact in fp16; an overflow saturates to the same 448 as the fp32
+// route): 8 instructions per pair instead of 11 -- this runs in every producer's inner loop.
 __device__ __forceinline__ void split_c8(float v0, float v1, uint32_t& hi, uint16_t& hi8, uint16_t& lo8) {
   hi = pack_f16x2_sat(v0, v1);
+  asm("{.reg .b32 t;\n\tmul.rn.f16x2 t, %1, %2;\n\tcvt.rn.satfinite.e4m3x2.f16x2 %0, t;}"
+      : "=h"(hi8)
+      : "r"(hi), "r"(0x44004400u));  // (4.0h, 4.0h)
   const float2 h = unpack_f16x2(hi);
-  hi8 = pack_e4m3x2(h.x * SVIT_C8_HI_SCALE, h.y * SVIT_C8_HI_SCALE);
   lo8 = pack_e4m3x2(__fsub_rn(v0, h.x) * SVIT_C8_LO_SCALE, __fsub_rn(v1, h.y) * SVIT_C8_LO_SCALE);
 }
 // 4 consecutive elements of a split-format array at element index i (i % 4 == 0)

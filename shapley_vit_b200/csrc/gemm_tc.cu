@@ -146,13 +146,6 @@ __device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* m
       "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
-// L2 prefetch of one box (no shared-memory destination): issued kPrefetchAhead k-blocks ahead of the ring, so that the
-// operand stream that comes from DRAM (A: the activations of the previous kernel, read once) is an L2 hit by the time
-// its stage is requested -- the ring alone (4-5 stages x 512 tensor cycles) is shorter than a loaded DRAM round trip
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
 // arrive (once the MMAs issued so far complete) on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
   asm volatile(
@@ -256,7 +249,6 @@ struct TcShape {
   int mode;       // svit_operand_format of the operands: the schedule of the K loop
   int nk_main;    // k-blocks of one fp16 / tf32 pass (128 bytes of K each)
   int nk_aux;     // C8: k-blocks (128 e4m3 values of K) of one compensation pass
-  int prefetch_ahead;  // pair kernel: A k-blocks prefetched into L2 beyond the smem ring (0 = off)
 };
 
 // the operand planes (main, aux1, aux2) of A and of B; unused entries repeat the main plane
@@ -542,6 +534,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& e, int g, int m_sl
 // stream is neither loaded into nor stored from the SM, and nothing in the epilogue waits on HBM.
 // `stg` alternates between two tiles per warp: the reduce issued two chunks ago must have read its
 // tile before it is rewritten (cp.async.bulk.wait_group.read 1).  Rows >= M are clipped by the map.
+template <int RBUF>
 __device__ __forceinline__ void epilogue_chunk_reduce(const EpiArgs& e, const CUtensorMap* map_out, int g, int m_slab, int n,
                                                       float* v, uint8_t* stg, int lane, const float* bias_s) {
   if (e.bias) {
@@ -555,7 +548,10 @@ __device__ __forceinline__ void epilogue_chunk_reduce(const EpiArgs& e, const CU
       v[4 * i] = a.x, v[4 * i + 1] = a.y, v[4 * i + 2] = b.x, v[4 * i + 3] = b.y;
     }
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  if (lane == 0) {
+    if (RBUF == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
   __syncwarp();
   // fp32 tile, rows of 128 bytes, 16-byte chunk j of row r at chunk (j ^ (r & 7)) = TMA SWIZZLE_128B
   uint8_t* wbase = stg + lane * 128;
@@ -588,7 +584,7 @@ __device__ __forceinline__ void epilogue_row_ragged(const EpiArgs& e, int g, int
 // accumulator, each further residual fragment one chunk ahead.  (With the loads issued where they
 // are used, an L2 round trip per chunk sat on the epilogue's critical path and the tensor pipe
 // idled a third of the time: profiles/r03_gemm_qkv.)
-template <int BN, int MODE, int OFMT, class Arrive>
+template <int BN, int MODE, int OFMT, int RBUF = 2, class Arrive>
 __device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape& sh, int g, int m_slab, int n0, int half,
                                               int lane, uint32_t tmem_acc, uint8_t* stg, float* bias_s,
                                               uint64_t* tfull, uint32_t parity, Arrive arrive,
@@ -616,7 +612,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs& epi, const TcShape&
   tmem_ld_32x32_issue(t0, v0);
   auto chunk = [&](int n, float* v, const float4 (&res)[8], int c) {
     if (MODE == EPI_REDUCE) {
-      if (rows_ok) epilogue_chunk_reduce(epi, map_out, g, m_slab, n, v, stg + (c & 1) * kStagingPerWarp, lane, bias_s + 32 * c);
+      if (rows_ok) epilogue_chunk_reduce<RBUF>(epi, map_out, g, m_slab, n, v, stg + (c & (RBUF - 1)) * kStagingPerWarp, lane, bias_s + 32 * c);
       return;
     }
     if (n < sh.N && rows_ok) {
@@ -788,14 +784,17 @@ struct Cfg2 {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + NUM_BARS * 8 + 16 + 1024;
 };
 // the reduce mode double-buffers its staging tile (a TMA reduce reads it asynchronously) and gives up a stage for it
-template <int MODE> struct PairCfg { using type = Cfg2<5>; };
-template <> struct PairCfg<EPI_REDUCE> { using type = Cfg2<4, 2 * kStagingPerWarp>; };
+template <int MODE, int STAGES> struct PairCfg { using type = Cfg2<5>; };
+template <> struct PairCfg<EPI_REDUCE, 4> { using type = Cfg2<4, 2 * kStagingPerWarp>; };
+// ... or keeps all five stages with ONE staging tile per warp (the warp then waits for the previous reduce to have
+// read the tile before rewriting it)
+template <> struct PairCfg<EPI_REDUCE, 5> { using type = Cfg2<5, kStagingPerWarp>; };
 
 template <int KIND, int STAGES, int MODE, int OFMT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     gemm_tc2_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ CUtensorMap tma_out, const TcShape sh,
                     const EpiArgs epi, const uint32_t idesc) {
-  using C = typename PairCfg<MODE>::type;
+  using C = typename PairCfg<MODE, STAGES>::type;
   static_assert(C::STAGES == STAGES, "stage count is a function of the epilogue mode");
   constexpr int BN = C::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -843,38 +842,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const uint32_t full0 = mapa_u32(smem_u32(&full_bar[0]), 0);  // the leader's full barriers
     int s = 0;
     uint32_t ph = 0;
-    // look-ahead cursor of the L2 prefetch: (tile, k-block) kPrefetchAhead steps past the load cursor
-    int64_t pf_tile = pair;
-    int pf_kb = 0, pf_g = 0, pf_m0 = 0;
-    auto pf_decode = [&]() {
-      pf_g = (int)(pf_tile / tiles_per_group);
-      pf_m0 = (int)((pf_tile % tiles_per_group) / sh.tiles_n) * (2 * BM) + (int)rank * BM;
-    };
-    auto pf_step = [&]() {  // prefetch this CTA's A box of the cursor's k-block, advance the cursor
-      if (pf_tile >= sh.total_tiles) return;
-      if (elect_one()) {
-        int ia, ib, kc;
-        kstep<KIND>(sh, pf_kb, ia, ib, kc);
-        tma_prefetch_3d(&maps.a[ia], kc, pf_m0, sh.a_grouped ? pf_g : 0);
-      }
-      __syncwarp();
-      if (++pf_kb == sh.num_kb) {
-        pf_kb = 0, pf_tile += npairs;
-        if (pf_tile < sh.total_tiles) pf_decode();
-      }
-    };
-    const int ahead = sh.prefetch_ahead;
-    if (ahead > 0 && pf_tile < sh.total_tiles) {
-      pf_decode();
-      for (int i = 0; i < ahead + C::STAGES; ++i) pf_step();
-    }
     for (int64_t tile = pair; tile < sh.total_tiles; tile += npairs) {
       const int g = (int)(tile / tiles_per_group);
       const int rem = (int)(tile % tiles_per_group);
       const int m0 = (rem / sh.tiles_n) * (2 * BM) + (int)rank * BM;
       const int n0 = (rem % sh.tiles_n) * BN + (int)rank * (BN / 2);
       for (int kb = 0; kb < sh.num_kb; ++kb) {
-        if (ahead > 0) pf_step();
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
@@ -940,7 +913,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int rem = (int)(tile % tiles_per_group);
       const int m0 = (rem / sh.tiles_n) * (2 * BM) + (int)rank * BM, n0 = (rem % sh.tiles_n) * BN;
       const uint32_t te = tempty0 + 8u * acc;
-      epilogue_tile<BN, MODE, OFMT>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
+      epilogue_tile<BN, MODE, OFMT, C::kStg / kStagingPerWarp>(epi, sh, g, m0 + quarter * 32, n0, half, lane,
                         tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN), stg, bias_s, &tfull_bar[acc], aph,
                         [te] { mbar_arrive_cluster(te); }, &tma_out);
       if ((acc ^= 1) == 0) aph ^= 1;
@@ -998,10 +971,9 @@ int launch_tc(const TcMaps& maps, TcShape sh, const EpiArgs& epi, uint32_t idesc
   return SVIT_OK;
 }
 
-template <int KIND, int MODE, int OFMT>
+template <int KIND, int MODE, int OFMT, int STAGES = (MODE == EPI_REDUCE ? 4 : 5)>
 int launch_tc2s(const TcMaps& maps, TcShape sh, const EpiArgs& epi, uint32_t idesc, cudaStream_t stream) {
-  using C = typename PairCfg<MODE>::type;
-  constexpr int STAGES = C::STAGES;
+  using C = typename PairCfg<MODE, STAGES>::type;
   CUtensorMap mo = maps.a[0];  // only the reduce mode reads it
   if (MODE == EPI_REDUCE) {
     int rc = encode_map_3d(&mo, SVIT_F32, epi.out, (uint64_t)sh.N, (uint64_t)sh.M, (uint64_t)sh.G, (uint64_t)sh.N * 4,
@@ -1034,8 +1006,13 @@ int launch_tc2(const TcMaps& maps, const TcShape& sh, const EpiArgs& epi, uint32
   if (!epi.rowvec && !epi.residual && !remap) return launch_tc2f<KIND, EPI_DIRECT>(maps, sh, epi, idesc, stream);
   if (!epi.rowvec && epi.residual && !remap && !epi.gelu && epi.out_dtype == SVIT_F32) {
     // in place (out IS the residual): the add can be done by the L2 (TMA reduce-add)
-    if (!no_reduce && epi.residual == epi.out && (sh.G == 1 || epi.residual_gs == epi.out_gs))
-      return launch_tc2s<KIND, EPI_REDUCE, SVIT_FMT_PLAIN>(maps, sh, epi, idesc, stream);
+    if (!no_reduce && epi.residual == epi.out && (sh.G == 1 || epi.residual_gs == epi.out_gs)) {
+      // default: five stages, one staging tile (A/B in one session, scripts/r2_gpu4.sh: out-proj 462 -> 441 us, MLP-down
+      // and the bench step within the box's noise); SVIT_GEMM_REDUCE_STAGES=4 keeps the double-staged variant
+      static const bool five = [] { const char* e = getenv("SVIT_GEMM_REDUCE_STAGES"); return !(e && e[0] == '4'); }();
+      return five ? launch_tc2s<KIND, EPI_REDUCE, SVIT_FMT_PLAIN, 5>(maps, sh, epi, idesc, stream)
+                  : launch_tc2s<KIND, EPI_REDUCE, SVIT_FMT_PLAIN, 4>(maps, sh, epi, idesc, stream);
+    }
     return launch_tc2s<KIND, EPI_RESIDUAL, SVIT_FMT_PLAIN>(maps, sh, epi, idesc, stream);
   }
   return launch_tc2f<KIND, EPI_GENERIC>(maps, sh, epi, idesc, stream);
@@ -1087,8 +1064,6 @@ int gemm_tc(int precision, const Operand& A, int64_t a_off, int64_t a_gs, const 
   sh.nk_aux = mode == SVIT_FMT_C8 ? (K + 127) / 128 : 0;
   sh.num_kb = mode == SVIT_FMT_X3 ? 3 * sh.nk_main : sh.nk_main + 2 * sh.nk_aux;
   sh.a_grouped = a_gs ? 1 : 0;
-  static const int pf_env = [] { const char* e = getenv("SVIT_GEMM_PREFETCH"); return e ? atoi(e) : -1; }();
-  sh.prefetch_ahead = pf_env >= 0 ? pf_env : 8;
   SVIT_CHECK_ARG(b_gs != 0 || G == 1, "gemm_tc: B must be grouped when G > 1");
   // instruction descriptor: D fp32, A/B format, both K-major, N, M (format 0 is fp16 for kind::f16 and e4m3 for
   // kind::f8f6f4: the compensation passes of F16C8 use the same descriptor)

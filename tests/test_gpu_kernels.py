@@ -99,8 +99,9 @@ def test_aggregate_16bit_is_rounded_fp32_result(ops, dtype, N, C):
 @pytest.mark.parametrize("N,C,P", [(8, 8, 100_000), (3, 5, 1027), (16, 17, 70_001), (32, 16, 40_003)])
 @pytest.mark.parametrize("fmt_name", ["x3", "c8"])
 def test_aggregate_split_planes_are_the_split_of_the_fp32_result(ops, fmt_name, N, C, P):
-    """svit_aggregate_split: the planes are the exact split of the bit-exact fp32 aggregate (two-rounding arithmetic),
-    also at a column offset of a wider array and through the per-coalition base of the multi-round fold."""
+    """svit_aggregate_split: X3 planes are the exact split of the bit-exact fp32 aggregate (two-rounding arithmetic); C8
+    planes (16-bit-grade) are the split of the fused accumulation, <= a few fp32 ulp from it.  Also at a column offset of
+    a wider array and through the per-coalition base of the multi-round fold."""
     from shapley_vit_b200._lib import FMT_C8, FMT_X3
     from shapley_vit_b200.ops import OperandArray
 
@@ -119,14 +120,16 @@ def test_aggregate_split_planes_are_the_split_of_the_fp32_result(ops, fmt_name, 
         got.plane(k).copy_(out.plane(k)[:C, col0:col0 + P])
         assert torch.count_nonzero(out.plane(k)[:C, :col0].view(torch.uint8)) == 0      # nothing outside the window
         assert torch.count_nonzero(out.plane(k)[C].view(torch.uint8)) == 0
-    check_planes(got, ref, 0.0, exact=True)
+    exact = fmt == FMT_X3
+    ulps = 0.0 if exact else N * 2.0 ** -23 * float(ref.abs().max())      # fused fold: < 1 fp32 ulp per client
+    check_planes(got, ref, ulps, exact=exact)
     base = (gen(C, (P + 7) // 8 * 8, seed=77) * 0.02).cuda()
     ref2 = ops.aggregate_onto(deltas, base, r, torch.empty((C, (P + 7) // 8 * 8), device="cuda"), P=P)[:, :P].cpu()
     out2 = OperandArray((C, (P + 7) // 8 * 8), torch.float16, fmt, "cuda:0")
     ops.aggregate_onto(deltas, base, r, out2, P=P)
     for k in range(2 if fmt == FMT_X3 else 3):
         got.plane(k).copy_(out2.plane(k)[:, :P])
-    check_planes(got, ref2, 0.0, exact=True)
+    check_planes(got, ref2, ulps, exact=exact)
 
 
 def test_aggregate_rejects_misaligned(ops):
