@@ -158,6 +158,14 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
+// Debug aid (scripts/attn_split_trace.py): when set, CTA 0 records clock64() per phase of its first items.
+__device__ long long* g_att_split_trace = nullptr;
+constexpr int kTraceItems = 24, kTraceSlots = 16;
+#define ATT_TRACE(slot)                                                                      \
+  do {                                                                                       \
+    if (trace && lane == 0 && it < kTraceItems) trace[it * kTraceSlots + (slot)] = clock64(); \
+  } while (0)
+
 struct AttMaps {
   CUtensorMap q0[2], q1[2], kv[2];  // [hi, lo] planes of qkv: 128-row / R1-row query boxes, NK-row key / value boxes
   CUtensorMap o[3];                 // context planes: hi16, then lo16 (X3) or hi8, lo8 (C8)
@@ -303,6 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_split_kernel(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* const trace = blockIdx.x == 0 ? g_att_split_trace : nullptr;
 
   if (warp == kProducerWarp && lane == 0) {
     for (int p = 0; p < 2; ++p) {
@@ -412,9 +421,13 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_split_kernel(const _
     for (int64_t item = blockIdx.x; item < sh.items; item += gridDim.x, ++it) {
       const uint32_t par = (uint32_t)it & 1;
       issue_qk(0, par);
+      ATT_TRACE(8);
       if (it > 0) issue_pv(1, par ^ 1, false, true);
+      ATT_TRACE(9);
       issue_qk(1, par);
+      ATT_TRACE(10);
       issue_pv(0, par, true, false);
+      ATT_TRACE(11);
     }
     if (it > 0) {
       // the last O1 claims the shared O columns: group 0 must have drained the last O0 (inside the loop the next
@@ -437,11 +450,13 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_split_kernel(const _
       const uint32_t par = (uint32_t)it & 1;
       mbar_wait(&bars[B_SFULL0 + grp], par);
       tc_fence_after();
+      if (quarter == 0) ATT_TRACE(4 * grp + 0);
       float inv = 0.f;
       if (warp_valid) inv = softmax_row<NK>(tbuf, Tn, sl2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_PFULL0 + grp]);
+      if (quarter == 0) ATT_TRACE(4 * grp + 1);
 
       // ---- O = P V is on its way: make the staging tiles reusable meanwhile ----
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -449,6 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_split_kernel(const _
 
       mbar_wait(&bars[B_OFULL0 + grp], par);
       tc_fence_after();
+      if (quarter == 0) ATT_TRACE(4 * grp + 2);
       uint32_t o[64];
       {
         uint32_t* o0 = o;
@@ -514,6 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_split_kernel(const _
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
+      if (quarter == 0) ATT_TRACE(4 * grp + 3);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -617,3 +634,11 @@ int attention_split_tc(const Operand& qkv, const Operand& ctx, int64_t n_seq, in
 }
 
 }  // namespace svit
+
+// debug: device buffer of 24 x 16 int64 (or NULL to switch the trace off); not part of the public ABI
+extern "C" int svit_debug_attention_split_trace(void* device_buffer) {
+  using namespace svit;
+  long long* p = static_cast<long long*>(device_buffer);
+  SVIT_CUDA(cudaMemcpyToSymbol(g_att_split_trace, &p, sizeof(p)));
+  return SVIT_OK;
+}
