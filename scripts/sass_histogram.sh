@@ -23,7 +23,6 @@ row "UTCATOMSWS / alloc" "UTCATOMSWS" "tcgen05.alloc / dealloc"
 row "UTMALDG" "UTMALDG" "cp.async.bulk.tensor load (TMA)"
 row "UTMASTG" "UTMASTG" "cp.async.bulk.tensor store (TMA)"
 row "UTMAREDG" "UTMAREDG" "cp.reduce.async.bulk.tensor (TMA reduce-add into L2)"
-row "UTMAPF" "UTMAPF" "cp.async.bulk.prefetch.tensor (TMA prefetch into L2)"
 row "UBLKCP" "UBLKCP" "cp.async.bulk (1-D bulk copy, K1)"
 row "SYNCS" "SYNCS" "mbarrier operations"
 row "UCGABAR" "UCGABAR" "barrier.cluster"
