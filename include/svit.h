@@ -12,7 +12,9 @@
  *   svit_aggregate_onto   <- the per-round accumulation of compute_utilities_lazy
  *                            fed_client_contribution/utils_fed_shapley.py:146-196 (model_agg_lazy over a list)
  *   svit_patchify,
- *   svit_forward_batched  <- net(img).logits inside evaluation, federated_learning/utils.py:886
+ *   svit_forward_batched,
+ *   svit_forward_lora_batched
+ *                         <- net(img).logits inside evaluation, federated_learning/utils.py:886
  *                            (HF ViTForImageClassification built at start.py:258-267)
  *   svit_score, svit_score_records
  *                         <- argmax / correct / CrossEntropy(sum) in evaluation,
@@ -182,6 +184,25 @@ int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t vec_stride,
                          int64_t patches_row0, float* logits, int64_t logits_stride, int C, int B, void* workspace,
                          size_t workspace_bytes, svit_stream_t stream);
 
+/* The same forward for PEFT-LoRA coalition models over a FROZEN base (reference start.py:274-283: LoRA r = 16 on query /
+ * value, classifier in modules_to_save): every weight matrix is shared by all C coalitions -- ONE mat region, every
+ * GEMM takes one B operand for all groups -- and the wrapped projections add the per-coalition low-rank term
+ *     q = x Wq^T + bq + (alpha / r) (x A_q^T) B_q^T          (PEFT lora.Linear, eval mode; likewise v)
+ * as a K-extension of the shared QKV GEMM.  FedAvg averages A and B separately (they are state_dict entries), so the
+ * term is not linear in the coalition: the caller aggregates the factors (svit_aggregate / svit_aggregate_split on the
+ * packed LoRA rows) into
+ *   lora  device [C, lora_stride] in the plan's operand format (packed array of lora_alloc elements), per layer l at
+ *         element l * 256 * hidden:  Acat [64, hidden] (rows 0 .. r-1 = A_q, rows 32 .. 32+r-1 = A_v, others 0), then
+ *         Bext [3 * hidden, 64] (query rows: columns 0 .. r-1 = (alpha/r) B_q; value rows: columns 32 .. = (alpha/r) B_v;
+ *         key rows 0);  r <= 32
+ *   wmat_shared  device [mat_size] in the operand format (one row);  wvec as in svit_forward_batched (per coalition:
+ *         the classifier and any bias / LayerNorm parameter the clients did train). */
+int svit_forward_lora_batched(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat_shared,
+                              int64_t wmat_alloc, const void* lora, int64_t lora_stride, int64_t lora_alloc,
+                              const void* patches, int64_t patches_alloc, int64_t patches_row0, float* logits,
+                              int64_t logits_stride, int C, int B, void* workspace, size_t workspace_bytes,
+                              svit_stream_t stream);
+
 /* Device-side timing of the forward by kernel class, for roofline reporting: between _begin and
  * _end every launch of svit_forward_batched on this plan is bracketed by CUDA events on its
  * stream; _end waits for them and returns, per class, the summed duration, the summed
@@ -228,7 +249,7 @@ typedef struct svit_epilogue {
 
 /* For g < G: out[g] = epilogue( A[g] (M x K, row-major) * B[g]^T (B[g] is N x K, row-major) ).
  * A, B in the operand dtype of `precision`; out_dtype is SVIT_F32 or that operand dtype.
- * Group strides may be 0 (operand shared by all groups).  M_out = M unless rows_in > 0. */
+ * Group strides may be 0 (operand shared by all groups: A and, on the tensor-core precisions, B).  M_out = M unless rows_in > 0. */
 /* SVIT_PREC_F16X3 / SVIT_PREC_F16C8: A and B are packed operand arrays (svit_split_operand) of exactly
  * (a_gs ? G : 1) * M * K and G * N * K elements in the precision's format; out_dtype SVIT_F32 gives a plain fp32
  * result, out_dtype SVIT_F16 a packed operand array of G * M_out * N elements in the same format (no rowvec /
@@ -236,6 +257,13 @@ typedef struct svit_epilogue {
 int svit_gemm(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, void* out,
               int64_t out_gs, int out_dtype, int G, int M, int N, int K, const svit_epilogue* epi,
               svit_stream_t stream);
+
+/* out[g] = epilogue( A[g] B[g]^T + Ae[g] Be[g]^T ): svit_gemm with a K-EXTENSION of 64 columns -- Ae [G, M, 64] and
+ * Be [G, N, 64] in the operand format of `precision` (a tensor-core precision) -- accumulated in the same pass as
+ * extra k-blocks.  b_gs may be 0 (B shared by all groups): the per-group low-rank correction of a shared weight. */
+int svit_gemm_ext(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, const void* Ae,
+                  const void* Be, void* out, int64_t out_gs, int out_dtype, int G, int M, int N, int K,
+                  const svit_epilogue* epi, svit_stream_t stream);
 
 /* fp32 array of `elems` elements -> packed operand array (out_fmt = SVIT_FMT_X3 / SVIT_FMT_C8) of out_alloc >=
  * elems elements: what the producers of the forward (svit_aggregate_split, LayerNorm, the GEMM epilogues,

@@ -33,7 +33,7 @@ EXPORTS = [
     "svit_version", "svit_last_error", "svit_device_info", "svit_layout_sizes", "svit_layout_segment",
     "svit_aggregate", "svit_aggregate_onto", "svit_aggregate_split", "svit_plan_create", "svit_plan_destroy",
     "svit_plan_workspace_bytes", "svit_plan_operand_dtype", "svit_plan_operand_format", "svit_patchify",
-    "svit_forward_batched", "svit_score", "svit_score_records", "svit_gemm", "svit_split_operand", "svit_layernorm", "svit_attention",
+    "svit_forward_batched", "svit_forward_lora_batched", "svit_gemm_ext", "svit_score", "svit_score_records", "svit_gemm", "svit_split_operand", "svit_layernorm", "svit_attention",
     "svit_attention_split", "svit_plan_timing_begin", "svit_plan_timing_end",
 ]
 KERNEL_CLASSES = ("gemm", "attention", "layernorm", "forward")
@@ -109,6 +109,8 @@ def load() -> C.CDLL:
         "svit_plan_operand_format": (i32, [vp]),
         "svit_patchify": (i32, [vp, vp, vp, i64, i64, i64, vp]),
         "svit_forward_batched": (i32, [vp, vp, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32, vp, C.c_size_t, vp]),
+        "svit_forward_lora_batched": (i32, [vp, vp, i64, vp, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32, vp, C.c_size_t, vp]),
+        "svit_gemm_ext": (i32, [i32, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, C.POINTER(EpilogueC), vp]),
         "svit_score": (i32, [vp, i64, vp, i32, i64, i32, vp, vp, vp, i64, i32, vp]),
         "svit_score_records": (i32, [vp, i64, vp, i32, i64, i32, vp, i32, vp]),
         "svit_gemm": (i32, [i32, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, i32, C.POINTER(EpilogueC), vp]),

@@ -98,7 +98,19 @@ int gemm_simt(int operand_dtype, const void* A, int64_t a_gs, const void* B, int
               const EpiArgs& epi, cudaStream_t stream);
 // A / B: operand arrays in the format of `precision` (PLAIN for tf32 / bf16 / f16, X3 / C8 packed arrays for the
 // split precisions), a_off / b_off the element offset of the operand inside its array
+// K-extension of a grouped GEMM: out[g] = epilogue(A[g] B[g]^T + Ae[g] Be[g]^T) with Ae (M x 64) and Be (N x 64) in the
+// operand format of the precision, both grouped.  Used for the low-rank per-coalition correction on top of a shared
+// weight matrix (frozen-base LoRA): the correction rides the same accumulator as one more k-block per pass.
+struct GemmExt {
+  Operand A;
+  int64_t a_off, a_gs;
+  Operand B;
+  int64_t b_off, b_gs;
+};
+constexpr int kGemmExtK = 64;
+
+// b_gs == 0: B is shared by all groups (one [N, K] matrix).
 int gemm_tc(int precision, const Operand& A, int64_t a_off, int64_t a_gs, const Operand& B, int64_t b_off, int64_t b_gs, int G,
-            int M, int N, int K, const EpiArgs& epi, cudaStream_t stream);
+            int M, int N, int K, const EpiArgs& epi, cudaStream_t stream, const GemmExt* ext = nullptr);
 
 }  // namespace svit

@@ -40,7 +40,7 @@ struct svit_plan {
   bool force_simt = false;
   bool full_last_layer = false;  // SVIT_FULL_LAST_LAYER=1: compute every token of the last layer (A/B and tests)
   // workspace byte offsets for (max_c, max_b)
-  size_t off_x = 0, off_xn = 0, off_qkv = 0, off_ctx = 0, off_h = 0, ws_bytes = 0;
+  size_t off_x = 0, off_xn = 0, off_qkv = 0, off_ctx = 0, off_h = 0, off_t = 0, ws_bytes = 0;
   int fmt = 0;                    // svit_operand_format of the GEMM operands (weights, patches, Xn, CTX, H)
   int64_t rows_max = 0;           // max_c * max_b * T: the plane pitches of the activation arrays are rows_max * width
   // optional per-kernel-class device timing (svit_plan_timing_begin / _end)
@@ -100,13 +100,23 @@ struct Timed {
 };
 
 int gemm_dispatch(svit_plan* p, const Operand& A, int64_t a_off, int64_t a_gs, const Operand& B, int64_t b_off, int64_t b_gs,
-                  int G, int M, int N, int K, const EpiArgs& epi, cudaStream_t stream) {
-  Timed t(p, stream, SVIT_CLS_GEMM, 2.0 * G * M * (double)N * K);
+                  int G, int M, int N, int K, const EpiArgs& epi, cudaStream_t stream, const GemmExt* ext = nullptr) {
+  Timed t(p, stream, SVIT_CLS_GEMM, 2.0 * G * M * (double)N * (K + (ext ? kGemmExtK : 0)));
   if (p->precision == SVIT_PREC_F32 || (p->force_simt && p->fmt == SVIT_FMT_PLAIN)) {
     const int es = dtype_size(p->operand_dtype);
-    return gemm_simt(p->operand_dtype, A.plane(0, a_off, es), a_gs, B.plane(0, b_off, es), b_gs, G, M, N, K, epi, stream);
+    int rc = gemm_simt(p->operand_dtype, A.plane(0, a_off, es), a_gs, B.plane(0, b_off, es), b_gs, G, M, N, K, epi, stream);
+    if (rc || !ext) return rc;
+    // CUDA-core path: the K-extension as a second GEMM accumulating in place (plain output arrays only)
+    if (epi.out_dtype != p->operand_dtype && epi.out_dtype != SVIT_F32) SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "gemm: extension output dtype");
+    EpiArgs e2{};
+    e2.out = epi.out, e2.out_gs = epi.out_gs, e2.out_dtype = epi.out_dtype, e2.M = epi.M, e2.N = epi.N;
+    e2.residual_gs = epi.out_gs;
+    if (epi.out_dtype != SVIT_F32) SVIT_FAIL(SVIT_ERR_UNSUPPORTED, "gemm: the CUDA-core K-extension needs an fp32 output");
+    e2.residual = static_cast<const float*>(epi.out);
+    return gemm_simt(p->operand_dtype, ext->A.plane(0, ext->a_off, es), ext->a_gs, ext->B.plane(0, ext->b_off, es), ext->b_gs, G, M,
+                     N, kGemmExtK, e2, stream);
   }
-  return gemm_tc(p->precision, A, a_off, a_gs, B, b_off, b_gs, G, M, N, K, epi, stream);
+  return gemm_tc(p->precision, A, a_off, a_gs, B, b_off, b_gs, G, M, N, K, epi, stream, ext);
 }
 
 }  // namespace
@@ -161,6 +171,7 @@ extern "C" int svit_plan_create(const svit_vit_cfg* cfg, int precision, int max_
   p->off_qkv = take(rows * 3 * cfg->hidden * es);
   p->off_ctx = take(rows * cfg->hidden * es);
   p->off_h = take(rows * cfg->ff * es);
+  p->off_t = take(rows * kGemmExtK * es);  // LoRA path: T = Xn [A_q; A_v]^T, the A operand of the QKV K-extension
   p->ws_bytes = off;
   *out = p;
   return SVIT_OK;
@@ -195,11 +206,54 @@ extern "C" int svit_patchify(const svit_plan* plan, const float* images, void* p
   return patchify_at(plan->operand_dtype, images, dst, off, n, c.channels, c.image, c.patch, static_cast<cudaStream_t>(stream));
 }
 
+namespace svit {
+namespace {
+// per-coalition LoRA operand rows (svit_forward_lora_batched): layer l at element l * (64 h + 3h 64) of a row:
+// Acat [64, h] then Bext [3h, 64], both K-major, in the plan's operand format
+struct LoraArgs {
+  const void* rows;
+  int64_t stride, alloc;
+};
+int forward_impl(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat, int64_t mat_stride,
+                 int64_t wmat_alloc, const void* patches, int64_t patches_alloc, int64_t patches_row0, float* logits,
+                 int64_t logits_stride, int C, int B, void* workspace, size_t workspace_bytes, svit_stream_t stream_,
+                 const LoraArgs* lora);
+}  // namespace
+}  // namespace svit
+
 extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat,
                                     int64_t mat_stride, int64_t wmat_alloc, const void* patches, int64_t patches_alloc,
                                     int64_t patches_row0, float* logits, int64_t logits_stride, int C, int B,
                                     void* workspace, size_t workspace_bytes, svit_stream_t stream_) {
+  return svit::forward_impl(plan, wvec, vec_stride, wmat, mat_stride, wmat_alloc, patches, patches_alloc, patches_row0, logits,
+                            logits_stride, C, B, workspace, workspace_bytes, stream_, nullptr);
+}
+
+extern "C" int svit_forward_lora_batched(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat_shared,
+                                         int64_t wmat_alloc, const void* lora, int64_t lora_stride, int64_t lora_alloc,
+                                         const void* patches, int64_t patches_alloc, int64_t patches_row0, float* logits,
+                                         int64_t logits_stride, int C, int B, void* workspace, size_t workspace_bytes,
+                                         svit_stream_t stream_) {
   using namespace svit;
+  SVIT_CHECK_ARG(plan && lora, "svit_forward_lora_batched: null pointer");
+  const svit_vit_cfg& cfg = plan->lay.cfg;
+  const int64_t per_layer = (int64_t)kGemmExtK * cfg.hidden * 4;  // 64 h (Acat) + 3h 64 (Bext)
+  SVIT_CHECK_ARG(lora_stride >= per_layer * cfg.layers && lora_stride % 64 == 0,
+                 "svit_forward_lora_batched: lora_stride must cover layers * 256 * hidden elements and be a multiple of 64");
+  SVIT_CHECK_ARG(plan->fmt == SVIT_FMT_PLAIN || (lora_alloc % 16 == 0 && lora_alloc >= (int64_t)(C - 1) * lora_stride + per_layer * cfg.layers),
+                 "svit_forward_lora_batched: bad plane pitch for the LoRA rows");
+  if (!aligned16(lora)) SVIT_FAIL(SVIT_ERR_ALIGN, "svit_forward_lora_batched: lora must be 16-byte aligned");
+  LoraArgs la{lora, lora_stride, lora_alloc};
+  return forward_impl(plan, wvec, vec_stride, wmat_shared, 0, wmat_alloc, patches, patches_alloc, patches_row0, logits,
+                      logits_stride, C, B, workspace, workspace_bytes, stream_, &la);
+}
+
+namespace svit {
+namespace {
+int forward_impl(svit_plan* plan, const float* wvec, int64_t vec_stride, const void* wmat, int64_t mat_stride,
+                 int64_t wmat_alloc, const void* patches, int64_t patches_alloc, int64_t patches_row0, float* logits,
+                 int64_t logits_stride, int C, int B, void* workspace, size_t workspace_bytes, svit_stream_t stream_,
+                 const LoraArgs* lora) {
   SVIT_CHECK_ARG(plan && wvec && wmat && patches && logits && workspace, "svit_forward_batched: null pointer");
   SVIT_CHECK_ARG(C >= 1 && C <= plan->max_c && B >= 1 && B <= plan->max_b,
                  "svit_forward_batched: (C=%d, B=%d) exceeds the plan's (%d, %d)", C, B, plan->max_c, plan->max_b);
@@ -207,14 +261,16 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
                  workspace_bytes, plan->ws_bytes);
   const svit_vit_cfg& cfg = plan->lay.cfg;
   const Layout& L = plan->lay;
-  SVIT_CHECK_ARG(vec_stride >= L.vec_size && mat_stride >= L.mat_size && vec_stride % 64 == 0 && mat_stride % 64 == 0,
+  // mat_stride == 0 (LoRA path only): ONE weight matrix region shared by every coalition
+  SVIT_CHECK_ARG(vec_stride >= L.vec_size && (mat_stride >= L.mat_size || (lora && mat_stride == 0)) && vec_stride % 64 == 0 &&
+                     mat_stride % 64 == 0,
                  "svit_forward_batched: weight strides must be multiples of 64 and cover the layout");
   SVIT_CHECK_ARG(logits_stride >= (int64_t)B * cfg.n_cls, "svit_forward_batched: logits_stride too small");
   if (!aligned16(wvec) || !aligned16(wmat) || !aligned16(patches) || ((uintptr_t)workspace & 255))
     SVIT_FAIL(SVIT_ERR_ALIGN, "svit_forward_batched: weights/patches must be 16-byte and workspace 256-byte aligned");
   const int fmt = plan->fmt;
   const bool split = fmt != SVIT_FMT_PLAIN;
-  SVIT_CHECK_ARG(!split || (wmat_alloc % 16 == 0 && patches_alloc % 16 == 0 && wmat_alloc >= (int64_t)(C - 1) * mat_stride + L.mat_size),
+  SVIT_CHECK_ARG(!split || (wmat_alloc % 16 == 0 && patches_alloc % 16 == 0 && wmat_alloc >= (int64_t)(mat_stride ? C - 1 : 0) * mat_stride + L.mat_size),
                  "svit_forward_batched: bad plane pitches for the split-format weights / patches");
 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -228,6 +284,8 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
   const Operand QKV{ws + plan->off_qkv, split ? SVIT_FMT_X3 : SVIT_FMT_PLAIN, plan->rows_max * 3 * h};
   const Operand CTX{ws + plan->off_ctx, fmt, plan->rows_max * h};
   const Operand H{ws + plan->off_h, fmt, plan->rows_max * ff};
+  const Operand TT{ws + plan->off_t, fmt, plan->rows_max * kGemmExtK};  // [C, M, 64] (LoRA path)
+  const Operand LR{const_cast<void*>(lora ? lora->rows : nullptr), fmt, lora ? lora->alloc : 0};
   const Operand WM{const_cast<void*>(wmat), fmt, wmat_alloc};
   const Operand PA{const_cast<void*>(patches), fmt, patches_alloc};
   const int es = dtype_size(odt);
@@ -267,7 +325,19 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
       e.bias_gs = vec_stride;
       EpiArgs ea = make_epi(&e, QKV.base, (int64_t)M * 3 * h, odt, M, 3 * h);
       out_op(ea, QKV);
-      if ((rc = gemm_dispatch(plan, Xn, 0, xgs, WM, mat(SVIT_SEG_WQ, l), mat_stride, C, M, 3 * h, h, ea, stream))) return rc;
+      if (!lora) {
+        if ((rc = gemm_dispatch(plan, Xn, 0, xgs, WM, mat(SVIT_SEG_WQ, l), mat_stride, C, M, 3 * h, h, ea, stream))) return rc;
+      } else {
+        // PEFT lora.Linear on query / value (reference start.py:274-276): q = x Wq^T + bq + (alpha/r) (x A_q^T) B_q^T.
+        // T = Xn Acat^T (rank-64 block: rows 0.. of A_q, 32.. of A_v), then the shared-weight QKV GEMM with the
+        // K-extension T Bext^T (Bext rows of q / v hold the scaled B factors, the k rows are zero).
+        const int64_t lo = (int64_t)l * kGemmExtK * h * 4, tgs = (int64_t)M * kGemmExtK;
+        EpiArgs et = make_epi(nullptr, TT.base, tgs, odt, M, kGemmExtK);
+        out_op(et, TT);
+        if ((rc = gemm_dispatch(plan, Xn, 0, xgs, LR, lo, lora->stride, C, M, kGemmExtK, h, et, stream))) return rc;
+        const GemmExt ext{TT, 0, tgs, LR, lo + (int64_t)kGemmExtK * h, lora->stride};
+        if ((rc = gemm_dispatch(plan, Xn, 0, xgs, WM, mat(SVIT_SEG_WQ, l), 0, C, M, 3 * h, h, ea, stream, &ext))) return rc;
+      }
     }
     if (l == cfg.layers - 1 && !plan->full_last_layer) {
       // Last layer: the classifier reads only the [CLS] token (HF modeling_vit.py:641-642), so past
@@ -362,6 +432,8 @@ extern "C" int svit_forward_batched(svit_plan* plan, const float* wvec, int64_t 
   return head(X, xgs, wvec, vec_stride, L.find(SVIT_SEG_LNF_G), L.find(SVIT_SEG_LNF_B), L.find(SVIT_SEG_HEAD_W),
               L.find(SVIT_SEG_HEAD_B), logits, logits_stride, C, B, T, h, cfg.n_cls, cfg.ln_eps, stream);
 }
+}  // namespace
+}  // namespace svit
 
 extern "C" int svit_gemm(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, void* out,
                          int64_t out_gs, int out_dtype, int G, int M, int N, int K, const svit_epilogue* epi,
@@ -381,6 +453,24 @@ extern "C" int svit_gemm(int precision, const void* A, int64_t a_gs, const void*
   if (precision == SVIT_PREC_F32 || (fmt == SVIT_FMT_PLAIN && env && env[0] == '1'))
     return gemm_simt(odt, A, a_gs, B, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
   return gemm_tc(precision, a, 0, a_gs, b, 0, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int svit_gemm_ext(int precision, const void* A, int64_t a_gs, const void* B, int64_t b_gs, const void* Ae,
+                             const void* Be, void* out, int64_t out_gs, int out_dtype, int G, int M, int N, int K,
+                             const svit_epilogue* epi, svit_stream_t stream) {
+  using namespace svit;
+  SVIT_CHECK_ARG(A && B && Ae && Be && out, "svit_gemm_ext: null pointer");
+  SVIT_CHECK_ARG(G >= 1 && M >= 1 && N >= 1 && K >= 1, "svit_gemm_ext: bad sizes");
+  const int odt = operand_dtype_of(precision);
+  SVIT_CHECK_ARG(odt >= 0 && precision != SVIT_PREC_F32, "svit_gemm_ext: a tensor-core precision is required");
+  SVIT_CHECK_ARG(out_dtype == SVIT_F32 || out_dtype == odt, "svit_gemm_ext: out_dtype must be f32 or the operand dtype");
+  const int fmt = format_of_precision(precision);
+  EpiArgs ea = make_epi(epi, out, out_gs, out_dtype, M, N);
+  if (fmt != SVIT_FMT_PLAIN && out_dtype != SVIT_F32) set_out_format(ea, fmt, (int64_t)G * M * N);
+  const Operand a{const_cast<void*>(A), fmt, (int64_t)(a_gs ? G : 1) * M * K}, b{const_cast<void*>(B), fmt, (int64_t)(b_gs ? G : 1) * N * K};
+  const GemmExt ext{Operand{const_cast<void*>(Ae), fmt, (int64_t)G * M * kGemmExtK}, 0, (int64_t)M * kGemmExtK,
+                    Operand{const_cast<void*>(Be), fmt, (int64_t)G * N * kGemmExtK}, 0, (int64_t)N * kGemmExtK};
+  return gemm_tc(precision, a, 0, a_gs, b, 0, b_gs, G, M, N, K, ea, static_cast<cudaStream_t>(stream), &ext);
 }
 
 extern "C" int svit_plan_timing_begin(svit_plan* plan) {

@@ -246,36 +246,51 @@ struct TcShape {
   int tiles_m, tiles_n, num_kb;
   int64_t total_tiles;
   int a_grouped;  // 0: A shared by all groups
+  int b_grouped;  // 0: B shared by all groups (frozen-base LoRA: one weight matrix for every coalition)
   int mode;       // svit_operand_format of the operands: the schedule of the K loop
   int nk_main;    // k-blocks of one fp16 / tf32 pass (128 bytes of K each)
   int nk_aux;     // C8: k-blocks (128 e4m3 values of K) of one compensation pass
+  int nk_ext;     // k-blocks (one per pass) appended from the K-EXTENSION operands, 0 = none
 };
 
-// the operand planes (main, aux1, aux2) of A and of B; unused entries repeat the main plane
+// the operand planes (main, aux1, aux2) of A and of B; unused entries repeat the main plane.  ea / eb: the planes of the
+// K-extension operands (svit_gemm_ext: out = A B^T + A_ext B_ext^T, K_ext = 64, always grouped) -- a low-rank
+// per-group correction on top of a shared B rides the same accumulator as extra k-blocks.
 struct TcMaps {
   CUtensorMap a[3], b[3];
+  CUtensorMap ea[3], eb[3];
 };
 
-// Step kb of the K loop: planes of A and B it multiplies and the K coordinate (elements) of its 128-byte block.
-//   PLAIN  (A0, B0) x nk_main
-//   X3     (A0 hi, B1 lo) x nk, (A1 lo, B0 hi) x nk, (A0 hi, B0 hi) x nk          -- small terms first
-//   C8     (A1 hi8, B2 lo8) x nk_aux, (A2 lo8, B1 hi8) x nk_aux [kind::f8f6f4], then (A0, B0) x nk_main [kind::f16]
+// Step kb of the K loop: planes of A and B it multiplies, the K coordinate (elements) of its 128-byte block and
+// whether the block comes from the extension operands.  Per pass: the main k-blocks, then nk_ext extension blocks.
+//   PLAIN  (A0, B0)
+//   X3     (A0 hi, B1 lo), (A1 lo, B0 hi), (A0 hi, B0 hi)                           -- small terms first
+//   C8     (A1 hi8, B2 lo8), (A2 lo8, B1 hi8) [kind::f8f6f4, 128 values per block], then (A0, B0) [kind::f16]
 template <int KIND>
-__device__ __forceinline__ void kstep(const TcShape& sh, int kb, int& ia, int& ib, int& kc) {
+__device__ __forceinline__ void kstep(const TcShape& sh, int kb, int& ia, int& ib, int& kc, bool& ext) {
   constexpr int BKE = KIND == 0 ? 64 : 32;
-  ia = 0, ib = 0, kc = kb * BKE;
-  if (KIND != 0 || sh.mode == SVIT_FMT_PLAIN) return;
-  if (sh.mode == SVIT_FMT_X3) {
-    const int nk = sh.nk_main;
-    if (kb < nk) ib = 1;
-    else if (kb < 2 * nk) ia = 1, kc = (kb - nk) * 64;
-    else kc = (kb - 2 * nk) * 64;
-  } else {
-    const int n8 = sh.nk_aux;
-    if (kb < n8) ia = 1, ib = 2, kc = kb * 128;
-    else if (kb < 2 * n8) ia = 2, ib = 1, kc = (kb - n8) * 128;
-    else kc = (kb - 2 * n8) * 64;
+  const int ne = sh.nk_ext, len_main = sh.nk_main + ne;
+  ia = 0, ib = 0, ext = false;
+  int pos = kb;
+  if (KIND == 0 && sh.mode == SVIT_FMT_X3) {
+    const int p = kb / len_main;
+    pos = kb - p * len_main;
+    if (p == 0) ib = 1;
+    else if (p == 1) ia = 1;
+  } else if (KIND == 0 && sh.mode == SVIT_FMT_C8) {
+    const int len_aux = sh.nk_aux + ne;
+    if (kb < 2 * len_aux) {
+      const int p = kb >= len_aux ? 1 : 0;
+      pos = kb - p * len_aux;
+      ia = p ? 2 : 1, ib = p ? 1 : 2;
+      ext = pos >= sh.nk_aux;
+      kc = ext ? 0 : pos * 128;  // (the extension holds 64 values: the rest of its 128-byte block reads as zeros)
+      return;
+    }
+    pos = kb - 2 * len_aux;
   }
+  ext = pos >= sh.nk_main;
+  kc = ext ? (pos - sh.nk_main) * BKE : pos * BKE;
 }
 
 // ---- packed fp32x2 arithmetic (FFMA2: two IEEE fp32 FMAs per issue slot on sm_100) ------------
@@ -697,9 +712,10 @@ __global__ void __launch_bounds__(kThreads, 1)
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
           int ia, ib, kc;
-          kstep<KIND>(sh, kb, ia, ib, kc);
-          tma_load_3d(sa, &maps.a[ia], &full_bar[s], kc, m0, sh.a_grouped ? g : 0);
-          tma_load_3d(sa + C::A_BYTES, &maps.b[ib], &full_bar[s], kc, n0, g);
+          bool ext;
+          kstep<KIND>(sh, kb, ia, ib, kc, ext);
+          tma_load_3d(sa, ext ? &maps.ea[ia] : &maps.a[ia], &full_bar[s], kc, m0, (ext || sh.a_grouped) ? g : 0);
+          tma_load_3d(sa + C::A_BYTES, ext ? &maps.eb[ib] : &maps.b[ib], &full_bar[s], kc, n0, (ext || sh.b_grouped) ? g : 0);
         }
         __syncwarp();
         if (++s == C::STAGES) s = 0, ph ^= 1;
@@ -709,7 +725,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     int s = 0, acc = 0;
     uint32_t ph = 0, aph = 0;
     const uint64_t adesc0 = umma_desc(smem_u32(smem)), bdesc0 = umma_desc(smem_u32(smem) + C::A_BYTES);
-    const int naux = (KIND == 0 && sh.mode == SVIT_FMT_C8) ? 2 * sh.nk_aux : 0;  // e4m3 compensation k-blocks come first
+    const int naux = (KIND == 0 && sh.mode == SVIT_FMT_C8) ? 2 * (sh.nk_aux + sh.nk_ext) : 0;  // e4m3 compensation k-blocks come first
     for (int64_t tile = blockIdx.x; tile < sh.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], aph ^ 1);
       tc_fence_after();
@@ -853,9 +869,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           uint8_t* sa = smem + (size_t)s * C::STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::STAGE_BYTES);
           int ia, ib, kc;
-          kstep<KIND>(sh, kb, ia, ib, kc);
-          tma_load_3d_pair(sa, &maps.a[ia], full0 + 8u * s, kc, m0, sh.a_grouped ? g : 0);
-          tma_load_3d_pair(sa + C::A_BYTES, &maps.b[ib], full0 + 8u * s, kc, n0, g);
+          bool ext;
+          kstep<KIND>(sh, kb, ia, ib, kc, ext);
+          tma_load_3d_pair(sa, ext ? &maps.ea[ia] : &maps.a[ia], full0 + 8u * s, kc, m0, (ext || sh.a_grouped) ? g : 0);
+          tma_load_3d_pair(sa + C::A_BYTES, ext ? &maps.eb[ib] : &maps.b[ib], full0 + 8u * s, kc, n0,
+                           (ext || sh.b_grouped) ? g : 0);
         }
         __syncwarp();
         if (++s == C::STAGES) s = 0, ph ^= 1;
@@ -866,7 +884,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       int s = 0, acc = 0;
       uint32_t ph = 0, aph = 0;
       const uint64_t adesc0 = umma_desc(smem_u32(smem)), bdesc0 = umma_desc(smem_u32(smem) + C::A_BYTES);
-      const int naux = (KIND == 0 && sh.mode == SVIT_FMT_C8) ? 2 * sh.nk_aux : 0;  // e4m3 compensation k-blocks come first
+      const int naux = (KIND == 0 && sh.mode == SVIT_FMT_C8) ? 2 * (sh.nk_aux + sh.nk_ext) : 0;  // e4m3 compensation k-blocks come first
       for (int64_t tile = pair; tile < sh.total_tiles; tile += npairs) {
         mbar_wait(&tempty_bar[acc], aph ^ 1);
         tc_fence_after();
@@ -1028,7 +1046,7 @@ int launch_tc1(const TcMaps& maps, const TcShape& sh, const EpiArgs& epi, uint32
 }  // namespace
 
 int gemm_tc(int precision, const Operand& A, int64_t a_off, int64_t a_gs, const Operand& B, int64_t b_off, int64_t b_gs, int G,
-            int M, int N, int K, const EpiArgs& epi, cudaStream_t stream) {
+            int M, int N, int K, const EpiArgs& epi, cudaStream_t stream, const GemmExt* ext) {
   const int mode = format_of_precision(precision);  // operand format = schedule of the K loop
   const int dtype = precision == SVIT_PREC_TF32 ? SVIT_F32 : precision == SVIT_PREC_BF16 ? SVIT_BF16 : SVIT_F16;
   SVIT_CHECK_ARG(precision == SVIT_PREC_TF32 || precision == SVIT_PREC_BF16 || precision == SVIT_PREC_F16 || mode != SVIT_FMT_PLAIN,
@@ -1056,15 +1074,25 @@ int gemm_tc(int precision, const Operand& A, int64_t a_off, int64_t a_gs, const 
   int rc;
   if ((rc = make_plane_maps(maps.a, dtype, A, a_off, M, K, a_gs ? G : 1, a_gs, BM))) return rc;
   if ((rc = make_plane_maps(maps.b, dtype, B, b_off, N, K, b_gs ? G : 1, b_gs, pair ? BN / 2 : BN))) return rc;
+  for (int i = 0; i < 3; ++i) maps.ea[i] = maps.a[i], maps.eb[i] = maps.b[i];
+  if (ext) {
+    SVIT_CHECK_ARG(ext->A.fmt == mode && ext->B.fmt == mode && ext->a_gs % 16 == 0 && ext->b_gs % 16 == 0 && ext->a_off % 16 == 0 &&
+                       ext->b_off % 16 == 0 && (G == 1 || (ext->a_gs && ext->b_gs)),
+                   "gemm_tc: the K-extension operands must be grouped arrays in the precision's format, 16-element aligned");
+    if ((rc = make_plane_maps(maps.ea, dtype, ext->A, ext->a_off, M, kGemmExtK, G, ext->a_gs, BM))) return rc;
+    if ((rc = make_plane_maps(maps.eb, dtype, ext->B, ext->b_off, N, kGemmExtK, G, ext->b_gs, pair ? BN / 2 : BN))) return rc;
+  }
   TcShape sh{};
   sh.G = G, sh.M = M, sh.N = N, sh.K = K;
   const int bk = 128 / es;
   sh.mode = mode;
   sh.nk_main = (K + bk - 1) / bk;
   sh.nk_aux = mode == SVIT_FMT_C8 ? (K + 127) / 128 : 0;
-  sh.num_kb = mode == SVIT_FMT_X3 ? 3 * sh.nk_main : sh.nk_main + 2 * sh.nk_aux;
+  sh.nk_ext = ext ? kGemmExtK / bk : 0;  // (one k-block per pass; two for tf32)
+  sh.num_kb = mode == SVIT_FMT_X3 ? 3 * (sh.nk_main + sh.nk_ext)
+                                  : (sh.nk_main + sh.nk_ext) + (mode == SVIT_FMT_C8 ? 2 * (sh.nk_aux + sh.nk_ext) : 0);
   sh.a_grouped = a_gs ? 1 : 0;
-  SVIT_CHECK_ARG(b_gs != 0 || G == 1, "gemm_tc: B must be grouped when G > 1");
+  sh.b_grouped = b_gs ? 1 : 0;
   // instruction descriptor: D fp32, A/B format, both K-major, N, M (format 0 is fp16 for kind::f16 and e4m3 for
   // kind::f8f6f4: the compensation passes of F16C8 use the same descriptor)
   const uint32_t fmt = precision == SVIT_PREC_TF32 ? 2u : precision == SVIT_PREC_BF16 ? 1u : 0u;

@@ -170,6 +170,10 @@ class CoalitionEngine:
         ops.aggregate(deltas[:, :V], w0v, ratios, out=self.wvec[:Cn], P=V)
         ops.aggregate(deltas[:, V:], w0m, ratios, out=self.wmat, P=Mz)
 
+    def _forward(self, Cn: int, row0: int, n_images: int, logits: torch.Tensor, image_offset: int) -> None:
+        """One svit_forward_batched launch sequence (overridden by the shared-weight LoRA engine)."""
+        self.plan.forward(self.wvec[:Cn], self.wmat, self.patches, row0, n_images, logits, image_offset=image_offset)
+
     def _run_batch(self, ratio_rows: Sequence[Sequence[float]], image_range: Optional[Tuple[int, int]] = None,
                    records: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         """One batch of <= coalition_batch coalitions given their dense ratio rows, scored on the validation
@@ -192,7 +196,7 @@ class CoalitionEngine:
         lo, hi = image_range if image_range is not None else (0, self.n_val)
         for s in range(lo, hi, self.image_chunk):
             b = min(self.image_chunk, hi - s)
-            self.plan.forward(self.wvec[:Cn], self.wmat, self.patches, s * npch, b, logits, image_offset=s)
+            self._forward(Cn, s * npch, b, logits, s)
         self.kernel_launches += 2 + ((hi - lo + self.image_chunk - 1) // self.image_chunk) * (3 + 7 * cfg.layers) + 1
         if records is not None:
             if hi > lo:

@@ -97,6 +97,38 @@ def pack_lora(cfg: VitConfig, lora: LoraDict, r: int, scaling: float, out: Optio
     return out
 
 
+EXT_K = 64   # kGemmExtK: columns of the K-extension block (query factors in 0 .. r-1, value factors in 32 .. 32+r-1)
+
+
+def pack_lora_ext(cfg: VitConfig, lora: LoraDict, r: int, scaling: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One fp32 row in the layout svit_forward_lora_batched reads (include/svit.h): per layer Acat [64, h] (rows 0 .. r-1 =
+    A_q, rows 32 .. 32+r-1 = A_v) then Bext [3h, 64] (query rows: columns 0 .. r-1 = scaling * B_q; value rows: columns
+    32 .. = scaling * B_v).  The zero padding is part of the row, so K1 on these rows (entry-wise FedAvg of A and of B,
+    as the reference aggregates the PEFT state_dict) yields the operand arrays directly."""
+    h = cfg.hidden
+    if r > 32:
+        raise ValueError("LoRA rank <= 32 supported by the K-extension path")
+    per = EXT_K * h * 4
+    if out is None:
+        out = torch.zeros(cfg.layers * per, dtype=torch.float32)
+    else:
+        out.zero_()
+    for (layer, target, ab), v in lora.items():
+        v = v.detach().to(torch.float32)
+        c0 = 0 if target == "query" else 32
+        base = layer * per
+        if ab == "A":
+            if tuple(v.shape) != (r, h):
+                raise ValueError(f"lora_A of layer {layer} {target}: expected {(r, h)}, got {tuple(v.shape)}")
+            out[base:base + EXT_K * h].view(EXT_K, h)[c0:c0 + r].copy_(v)
+        else:
+            if tuple(v.shape) != (h, r):
+                raise ValueError(f"lora_B of layer {layer} {target}: expected {(h, r)}, got {tuple(v.shape)}")
+            rows0 = 0 if target == "query" else 2 * h
+            out[base + EXT_K * h:base + per].view(3 * h, EXT_K)[rows0:rows0 + h, c0:c0 + r].copy_(v * scaling)
+    return out
+
+
 def merged_state_dict(sd, lora_alpha: float = 8.0) -> "OrderedDict[str, torch.Tensor]":
     """Plain HF-keyed state_dict of ONE PEFT-LoRA model with W + (alpha / r) B A folded into the wrapped
     projections (host fp32): what scoring a single explicit model needs (``fl.evaluation``)."""
@@ -118,7 +150,10 @@ class LoraCoalitionEngine(CoalitionEngine):
     """CoalitionEngine for PEFT-LoRA client models: same evaluate()/Game interface, state_dicts with LoRA keys."""
 
     def __init__(self, cfg: VitConfig, w0_sd, delta_sds: Sequence[dict], images, labels=None, lora_alpha: float = 8.0,
-                 **kw):
+                 shared_base: Optional[bool] = None, **kw):
+        """``shared_base``: None = take the shared-weight forward (svit_forward_lora_batched) whenever the base weight
+        matrices are frozen (no client moved them) and the rank is <= 32; False = always merge the factors into dense
+        per-coalition weights (the general path: trained base, or an A/B reference for the shared one)."""
         hf0, l0 = split_state_dict(w0_sd)
         parts = [split_state_dict(d) for d in delta_sds]
         self.r = lora_rank(l0)
@@ -142,7 +177,20 @@ class LoraCoalitionEngine(CoalitionEngine):
             # the author's case: nothing but LoRA (and the vec region: classifier, biases) differs between clients
             self.base_frozen = not bool(self.deltas[:, V:].any().item())
             self._eye = torch.eye(cb, dtype=torch.float32)               # K1 as a row-wise cast: out[c] = 1 * rows[c]
-            if self.base_frozen:
+            self.shared = self.base_frozen and self.r <= 32 and shared_base is not False and cfg.hidden % 64 == 0
+            if self.shared:
+                # N1: the K / out-proj / MLP weights (and W_q, W_v under the LoRA term) are the same
+                # for every coalition: ONE mat-region row, shared B operands; the factors ride the QKV GEMM as a K-extension
+                ext = torch.empty((n + 1, L * EXT_K * h * 4), dtype=torch.float32, pin_memory=True)
+                pack_lora_ext(cfg, l0, r, self.scaling, out=ext[n])
+                for j, p in enumerate(parts):
+                    pack_lora_ext(cfg, p[1], r, self.scaling, out=ext[j])
+                edev = ext.to(self.device)
+                self.ext_deltas, self.ext_w0 = edev[:n], edev[n]
+                self.lora_rows = self.plan.operand_array((cb, ext.shape[1]))
+                self.wmat_shared = self.plan.operand_array((1, self.lay.mat_size))
+                ops.aggregate(self.w0[V:].unsqueeze(0), None, torch.ones((1, 1)), out=self.wmat_shared, P=self.lay.mat_size)
+            elif self.base_frozen:
                 ops.aggregate(self.w0[V:].unsqueeze(0), None, torch.ones((cb, 1)), out=self.wmat, P=self.lay.mat_size)
                 self.qv_base = torch.stack([self.w0[V + o:V + o + h * h] for o in self.qv_off])   # [n_proj, h*h] fp32
             torch.cuda.synchronize(self.device)
@@ -152,6 +200,12 @@ class LoraCoalitionEngine(CoalitionEngine):
         h, r, V, Mz = cfg.hidden, self.r, lay.vec_size, lay.mat_size
         hh = h * h
         ops.aggregate(self.deltas[:, :V], self.w0[:V], ratios, out=self.wvec[:Cn], P=V)
+        if self.shared:
+            # entry-wise FedAvg of the factors (A and B separately, as the reference averages the PEFT state_dict),
+            # written straight as the operand rows of the K-extension: one K1 launch, ~2 % of a dense model's bytes
+            ops.aggregate(self.ext_deltas, self.ext_w0, ratios, out=self.lora_rows)
+            self.kernel_launches += 2
+            return
         qv = self.qv32[:Cn]
         if self.base_frozen:
             qv.copy_(self.qv_base)                                   # W_0 blocks, shared by every coalition
@@ -169,10 +223,21 @@ class LoraCoalitionEngine(CoalitionEngine):
             ops.aggregate(qv[:, i], None, eye, out=self.wmat, P=hh, col0=o)
         self.kernel_launches += 2 + self.n_proj + (0 if self.base_frozen else 1 + self.n_proj)
 
+    def _forward(self, Cn: int, row0: int, n_images: int, logits: torch.Tensor, image_offset: int) -> None:
+        if self.shared:
+            self.plan.forward_lora(self.wvec[:Cn], self.wmat_shared, self.lora_rows, self.patches, row0, n_images, logits,
+                                   image_offset=image_offset)
+        else:
+            super()._forward(Cn, row0, n_images, logits, image_offset)
+
     def evaluate_state_dict(self, sd) -> Tuple[int, float]:
         """Score one explicit model; PEFT-keyed state_dicts are merged on the host first."""
-        out = super().evaluate_state_dict(merged_state_dict(sd, self.scaling * self.r) if is_lora_state_dict(sd) else sd)
-        if self.base_frozen:   # the call went through wmat[0]: restore the W_0 rows the frozen-base path relies on
+        shared, self.shared = self.shared, False      # an explicit dense model goes through the dense forward
+        try:
+            out = super().evaluate_state_dict(merged_state_dict(sd, self.scaling * self.r) if is_lora_state_dict(sd) else sd)
+        finally:
+            self.shared = shared
+        if self.base_frozen and not self.shared:   # the call went through wmat[0]: restore the W_0 rows the frozen-base path relies on
             V = self.lay.vec_size
             ops.aggregate(self.w0[V:].unsqueeze(0), None, torch.ones((1, 1)), out=self.wmat, P=self.lay.mat_size)
         return out

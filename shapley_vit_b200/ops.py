@@ -288,6 +288,34 @@ def gemm(precision: int, A: torch.Tensor, B: torch.Tensor, bias: Optional[torch.
     return out_arr if out_arr is not None else out
 
 
+def gemm_ext(precision: int, A: torch.Tensor, B: torch.Tensor, Ae: torch.Tensor, Be: torch.Tensor,
+             bias: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32):
+    """out[g] = A[g] @ B[g or 0].T + Ae[g] @ Be[g].T (+ bias): svit_gemm_ext.  A [G, M, K], B [G | 1, N, K], Ae [G, M, 64],
+    Be [G, N, 64] fp32 CUDA tensors (converted to the precision's operand format here); fp32 or operand-format output."""
+    for t in (A, B, Ae, Be):
+        _cuda(t, "operand")
+    G, M, K = A.shape
+    N = B.shape[1]
+    fmt = OPERAND_FORMAT[precision]
+    odt = TORCH_DTYPE[_lib.OPERAND_DTYPE[precision]]
+    conv = lambda t: OperandArray.from_float(t.contiguous().float(), fmt, odt)
+    a, b, ae, be = conv(A), conv(B), conv(Ae), conv(Be)
+    if out_dtype == torch.float32:
+        out_arr, out = None, torch.zeros((G, M, N), dtype=torch.float32, device=A.device)
+        optr = _ptr(out)
+    else:
+        out_arr = OperandArray((G, M, N), odt, fmt, A.device)
+        out, optr = out_arr.plane(0), C.c_void_p(out_arr.ptr)
+    epi = EpilogueC()
+    if bias is not None:
+        bias = bias.contiguous()
+        epi.bias, epi.bias_gs = bias.data_ptr(), N
+    check(_lib.load().svit_gemm_ext(precision, C.c_void_p(a.ptr), M * K, C.c_void_p(b.ptr), N * K if B.shape[0] == G else 0,
+                                    C.c_void_p(ae.ptr), C.c_void_p(be.ptr), optr, M * N, SVIT_DTYPE[out.dtype], G, M, N, K,
+                                    C.byref(epi), _stream(A)))
+    return out_arr if out_arr is not None else out
+
+
 class Plan:
     """Owner of an ``svit_plan`` plus its torch-allocated workspace."""
 
@@ -351,4 +379,19 @@ class Plan:
             self._h, _ptr(wvec), wvec.stride(0), C.c_void_p(wmat.ptr), wmat.shape[1], wmat.alloc, C.c_void_p(patches.ptr),
             patches.alloc, row0, C.c_void_p(lptr), logits.stride(0), Cn, n_images, _ptr(self.workspace),
             self.workspace_bytes, _stream(wvec)))
+        return logits
+
+    def forward_lora(self, wvec: torch.Tensor, wmat_shared: OperandArray, lora: OperandArray, patches: OperandArray, row0: int,
+                     n_images: int, logits: torch.Tensor, image_offset: int = 0) -> torch.Tensor:
+        """``forward`` for PEFT-LoRA coalition models over a frozen base: ``wmat_shared`` is ONE mat-region row shared by
+        every coalition, ``lora`` the per-coalition [C, layers * 256 * hidden] rows (Acat | Bext per layer, include/svit.h)."""
+        _cuda(wvec, "wvec", torch.float32)
+        if wmat_shared.fmt != self.operand_format or patches.fmt != self.operand_format or lora.fmt != self.operand_format:
+            raise ValueError("wmat / lora / patches are not in this plan's operand format")
+        Cn = wvec.shape[0]
+        lptr = logits.data_ptr() + image_offset * self.cfg.n_cls * 4
+        check(_lib.load().svit_forward_lora_batched(
+            self._h, _ptr(wvec), wvec.stride(0), C.c_void_p(wmat_shared.ptr), wmat_shared.alloc, C.c_void_p(lora.ptr), lora.shape[1],
+            lora.alloc, C.c_void_p(patches.ptr), patches.alloc, row0, C.c_void_p(lptr), logits.stride(0), Cn, n_images,
+            _ptr(self.workspace), self.workspace_bytes, _stream(wvec)))
         return logits

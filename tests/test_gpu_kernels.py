@@ -456,3 +456,23 @@ def test_gemm_tcgen05_epilogues(ops, prec_name):
     want = ref_gemm(A.float(), B.float(), bias, residual=X.cpu())
     ops.gemm(prec, A.cuda(), B.cuda(), bias=bias.cuda(), residual=X, out_dtype=torch.float32, out=X)
     assert (X.cpu().double() - want).abs().max() < tol
+
+
+# ----------------------------------------------------------------------------- K-extension GEMM (N1)
+@pytest.mark.parametrize("prec_name,tol", [("f16", 6e-3), ("f16x3", 3e-5), ("f16c8", 3e-4), ("tf32", 8e-3)])
+@pytest.mark.parametrize("shape", [(3, 394, 768, 768, True), (2, 130, 192, 192, False), (2, 512, 2304, 768, True)])
+def test_gemm_k_extension_and_shared_b(ops, prec_name, tol, shape):
+    """svit_gemm_ext: out[g] = A[g] B^T + Ae[g] Be[g]^T + bias with B shared by all groups (or grouped): the low-rank
+    per-coalition correction of the LoRA path as extra k-blocks of the same accumulator; pair and one-CTA kernels."""
+    from shapley_vit_b200._lib import PRECISIONS
+
+    G, M, N, K, shared = shape
+    A, B = gen(G, M, K, seed=21), gen(1 if shared else G, N, K, seed=22) * 0.05
+    Ae, Be = gen(G, M, 64, seed=23) * 0.3, gen(G, N, 64, seed=24) * 0.1
+    Ae[:, :, 40:] = 0                                                   # (the LoRA blocks leave columns unused)
+    bias = gen(G, N, seed=25)
+    got = ops.gemm_ext(PRECISIONS[prec_name], A.cuda(), B.cuda(), Ae.cuda(), Be.cuda(), bias=bias.cuda()).cpu()
+    want = (A.double() @ B.double().transpose(1, 2) + Ae.double() @ Be.double().transpose(1, 2) + bias.double()[:, None, :]).float()
+    err = (got - want).abs().max().item()
+    print(f"gemm_ext[{prec_name}] {shape}: max err {err:.3e}")
+    assert err < tol * max(1.0, want.abs().max().item() / 4)

@@ -22,10 +22,10 @@ def peft_game(n_clients=3, n_val=96, seed=3, frozen=True, layers=2):
     return cfg, w0, deltas, synth.client_sizes(n_clients), images, labels
 
 
-def oracle_logits(cfg, w0, deltas, n_train, members, images):
+def oracle_logits(cfg, w0, deltas, n_train, members, images, r=R):
     sd = restate.coalition_state_dict(w0, deltas, n_train, list(members))     # every PEFT key, entry by entry
     hf, lo = restate.split_peft_state_dict(sd)
-    return restate.vit_forward(hf, cfg, images, lora=lo, lora_scaling=ALPHA / R), hf, lo
+    return restate.vit_forward(hf, cfg, images, lora=lo, lora_scaling=ALPHA / r), hf, lo
 
 
 def ratio_rows(coalitions, n_train):
@@ -73,8 +73,8 @@ def test_merged_projection_weights_match_oracle(frozen):
     cfg, w0, deltas, n_train, images, labels = peft_game(frozen=frozen)
     coalitions = [(0,), (1, 2), (0, 1, 2)]
     eng = lora.LoraCoalitionEngine(cfg, w0, deltas, images, labels, lora_alpha=ALPHA, precision="f32", coalition_batch=3,
-                                   image_chunk=32)
-    assert eng.base_frozen == frozen
+                                   image_chunk=32, shared_base=False)      # the dense-merge path
+    assert eng.base_frozen == frozen and not eng.shared
     got = eng.merged_rows(ratio_rows(coalitions, n_train)).cpu().double()
     for ci, S in enumerate(coalitions):
         _, hf, lo = oracle_logits(cfg, w0, deltas, n_train, S, images[:1])
@@ -93,6 +93,7 @@ def test_lora_coalition_logits_and_counts(prec, tol, frozen):
     coalitions = [(0,), (1,), (2,), (0, 1), (0, 2), (1, 2), (0, 1, 2)]
     eng = lora.LoraCoalitionEngine(cfg, w0, deltas, images, labels, lora_alpha=ALPHA, precision=prec, coalition_batch=4,
                                    image_chunk=32, keep_logits=True)
+    assert eng.shared == frozen                        # frozen base: ONE shared weight region + the K-extension (N1)
     rows = ratio_rows(coalitions, n_train)
     worst = 0.0
     for s0 in range(0, len(rows), 4):                  # two batches: the frozen matrix region must survive a batch
@@ -105,6 +106,34 @@ def test_lora_coalition_logits_and_counts(prec, tol, frozen):
                 assert int(correct[ci]) == int((want.argmax(1) == labels).sum())
     print(f"[lora {prec} frozen={frozen}] max |dlogit| = {worst:.3e}")
     assert worst < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("f32", 1e-5), ("f16x3", 3e-5), ("f16c8", 3e-4), ("f16", 8e-3)])
+def test_shared_weight_forward_equals_the_dense_merge(prec, tol):
+    """N1: with a frozen base the shared-weight forward (one mat region for every coalition, the factors as a
+    K-extension of the QKV GEMM: x W^T + (x A_S^T)(s B_S)^T) and the dense per-coalition merge W + s B_S A_S are the
+    same function; ViT-B geometry (pair GEMM kernels), rank 16 as in the reference's start.py:275."""
+    cfg = layout.vit_preset("base", image=224, n_cls=10, layers=2)
+    w0, clients = synth.make_peft_state_dicts(cfg, 3, seed=5, r=16, frozen_base=True)
+    deltas = [restate.get_difference_between_network_weights(sd, w0) for sd in clients]
+    n_train = synth.client_sizes(3)
+    images, labels = synth.make_val_set(cfg, 6, 5)
+    rows = ratio_rows([(0,), (1, 2), (0, 1, 2)], n_train)
+    out = {}
+    for shared in (None, False):
+        eng = lora.LoraCoalitionEngine(cfg, w0, deltas, images, labels, lora_alpha=ALPHA, precision=prec, coalition_batch=3,
+                                       image_chunk=6, keep_logits=True, shared_base=shared)
+        assert eng.shared == (shared is None)
+        out[shared] = (eng.evaluate(rows), eng.last_logits.cpu())
+        del eng
+    worst = (out[None][1] - out[False][1]).abs().max().item()
+    print(f"[lora shared vs dense, {prec}] max |dlogit| = {worst:.3e}")
+    assert worst < tol
+    if prec in ("f32", "f16x3"):
+        assert out[None][0][0] == out[False][0][0]
+    want, _, _ = oracle_logits(cfg, w0, deltas, n_train, (1, 2), images, r=16)   # and against the oracle's unmerged branch
+    assert (out[None][1][1] - want).abs().max().item() < max(tol, 2e-4)
 
 
 @pytest.mark.gpu
