@@ -49,6 +49,11 @@ def parse_args():
     ap.add_argument("--precision", default="f16c8", choices=["f16c8", "f16x3", "f32", "f16", "bf16", "tf32"],
                     help="f16c8 (default), f16x3, f32: parity modes (>= 99.9 %% top-1 agreement with fp32); "
                          "f16, bf16, tf32: single-pass throughput modes outside that gate")
+    ap.add_argument("--lora-rank", type=int, default=0,
+                    help="> 0: the clients are PEFT-LoRA models (rank r on query / value, classifier saved) over a FROZEN base "
+                         "(reference start.py:274-283): the shared-weight forward of SURVEY section 8(f) N1")
+    ap.add_argument("--lora-path", default="shared", choices=["shared", "dense"],
+                    help="with --lora-rank: shared-weight forward + K-extension (N1), or the dense per-coalition merge")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -68,6 +73,9 @@ def workload_name(a):
     cfg2 = (a.clients, a.vit, a.image, a.val, a.classes) == (8, "base", 224, 10000, 10)
     cfg4 = (a.clients, a.vit, a.image, a.coalition_batch) == (10, "large", 224, 32)
     tag = "BASELINE config 2" if cfg2 else "BASELINE config 4 geometry" if cfg4 else "not a BASELINE configuration"
+    if a.lora_rank:
+        tag += (f"; clients are PEFT-LoRA models, rank {a.lora_rank} on query / value over a frozen base, "
+                + ("dense per-coalition merge" if a.lora_path == "dense" else "shared-weight forward + K-extension (N1)"))
     return (f"{a.clients}-client FedAvg ViT-{a.vit}/16 @{a.image}px, exact-Shapley enumeration "
             f"({2 ** a.clients - 1} coalitions), {a.val}-image synthetic val set, {a.classes} classes ({tag})")
 
@@ -451,9 +459,9 @@ def run_ours(a):
     prec = _lib.PRECISIONS[a.precision]
 
     # ---- client weights: built on rank 0, broadcast once over NVLink (NCCL) -------------------
-    deltas = torch.empty((N, lay.total), dtype=torch.float32, device=dev)
+    deltas = torch.empty((N if not a.lora_rank else 0, lay.total), dtype=torch.float32, device=dev)
     w0 = torch.empty(lay.total, dtype=torch.float32, device=dev)
-    if rank == 0:
+    if rank == 0 and not a.lora_rank:
         w0_sd = synth.make_state_dict(cfg, a.seed)
         w0.copy_(layout.pack_state_dict(lay, w0_sd))
         row = torch.empty(lay.total, dtype=torch.float32).pin_memory()
@@ -476,8 +484,20 @@ def run_ours(a):
         images_host[s:s + n].copy_(torch.randn((n, cfg.channels, cfg.image, cfg.image), generator=g, device=dev))
     labels_host = torch.randint(0, cfg.n_cls, (a.val,), generator=g, device=dev).cpu()
     val = ValidationSet(cfg, images_host, labels_host, prec, dev)
-    eng = CoalitionEngine(cfg, w0, deltas, val, precision=prec, coalition_batch=Cb, image_chunk=a.image_chunk,
-                          device=dev)
+    if a.lora_rank:
+        # N1: every rank builds the same seeded PEFT state_dicts (frozen base); the engine aggregates A and B separately
+        from shapley_vit_b200 import lora as lora_mod
+
+        w0_sd, client_sds = synth.make_peft_state_dicts(cfg, N, a.seed, r=a.lora_rank)
+        delta_sds = [{k: c[k] - w0_sd[k] for k in c} for c in client_sds]
+        del client_sds
+        eng = lora_mod.LoraCoalitionEngine(cfg, w0_sd, delta_sds, val, lora_alpha=8.0, precision=prec, coalition_batch=Cb,
+                                           image_chunk=a.image_chunk, device=dev, shared_base=a.lora_path == "shared")
+        del delta_sds
+        deltas, w0 = eng.deltas, eng.w0
+    else:
+        eng = CoalitionEngine(cfg, w0, deltas, val, precision=prec, coalition_batch=Cb, image_chunk=a.image_chunk,
+                              device=dev)
     eng.profile = True
 
     # ---- coalition enumeration (exact Shapley order), FedAvg ratio rows -----------------------
@@ -600,7 +620,7 @@ def run_ours(a):
 
     # ---- the single-pass fp16 throughput mode on the same workload (outside the top-1 gate; reported, not the headline)
     throughput_mode = None
-    if ws == 1 and not a.no_throughput_mode and a.precision in ("f16c8", "f16x3"):
+    if ws == 1 and not a.no_throughput_mode and a.precision in ("f16c8", "f16x3") and not a.lora_rank:
         try:
             p16 = _lib.PRECISIONS["f16"]
             val16 = ValidationSet(cfg, images_host, labels_host, p16, dev)
@@ -622,7 +642,7 @@ def run_ours(a):
             throughput_mode = {"error": repr(e)}
 
     parity = None
-    if ws == 1 and not a.no_parity:
+    if ws == 1 and not a.no_parity and not a.lora_rank:
         try:
             parity = parity_leg(a, cfg, lay, deltas, w0, images_host, labels_host, dev, val_main=val)
         except Exception as e:  # never lose the throughput line to the parity leg
@@ -665,6 +685,9 @@ def run_ours(a):
     l_ms, l_bytes, l_n = timing["layernorm"]
     es = 2 if a.precision in ("f16", "bf16") else 4   # bytes per weight element over all planes
     agg_bytes = a.steps * (4.0 * lay.total * (N + 1) + (4.0 * lay.vec_size + es * lay.mat_size) * Cb)
+    if a.lora_rank and getattr(eng, "shared", False):   # vec region + the packed factor rows only
+        lw = eng.ext_deltas.shape[1]
+        agg_bytes = a.steps * (4.0 * (lay.vec_size + lw) * (N + 1) + (4.0 * lay.vec_size + es * lw) * Cb)
     breakdown = {
         "gemm_ms": g_ms, "attention_ms": a_ms, "attention_tflops": a_flops / (a_ms / 1e3) / 1e12 if a_ms else None,
         "layernorm_ms": l_ms, "layernorm_gbs": l_bytes / (l_ms / 1e3) / 1e9 if l_ms else None,

@@ -158,13 +158,18 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 
-// Debug aid (scripts/attn_split_trace.py): when set, CTA 0 records clock64() per phase of its first items.
+// Debug aid (scripts/attn_split_trace.py; build with -DSVIT_ATT_TRACE): CTA 0 records clock64() per phase of its first
+// items.  Compiled out by default: the instrumented kernel is 20 % slower (665 vs 553 us per 1 024 x 12 heads).
 __device__ long long* g_att_split_trace = nullptr;
+#ifdef SVIT_ATT_TRACE
 constexpr int kTraceItems = 24, kTraceSlots = 16;
 #define ATT_TRACE(slot)                                                                      \
   do {                                                                                       \
     if (trace && lane == 0 && it < kTraceItems) trace[it * kTraceSlots + (slot)] = clock64(); \
   } while (0)
+#else
+#define ATT_TRACE(slot) do { } while (0)
+#endif
 
 struct AttMaps {
   CUtensorMap q0[2], q1[2], kv[2];  // [hi, lo] planes of qkv: 128-row / R1-row query boxes, NK-row key / value boxes
@@ -311,7 +316,9 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_split_kernel(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef SVIT_ATT_TRACE
   long long* const trace = blockIdx.x == 0 ? g_att_split_trace : nullptr;
+#endif
 
   if (warp == kProducerWarp && lane == 0) {
     for (int p = 0; p < 2; ++p) {
