@@ -145,8 +145,9 @@ int svit_aggregate_onto(const float* deltas, int64_t delta_stride, const float* 
                         int C, svit_stream_t stream);
 
 /* The same aggregation written as a split-format packed operand array (the weight feed of SVIT_PREC_F16X3 /
- * SVIT_PREC_F16C8): the value that is split is the fp32 two-rounding result above (w0 + sum, or base[c] + sum
- * when `base` is given -- exactly one of w0 / base may be non-NULL, both NULL = zeros).
+ * SVIT_PREC_F16C8).  SVIT_FMT_X3 (~21 bits): the value that is split is the fp32 two-rounding result above; SVIT_FMT_C8
+ * (~16 bits): the fused accumulation of the 16-bit outputs (<= 1 fp32 ulp per client from it).  w0 + sum, or
+ * base[c] + sum when `base` is given -- exactly one of w0 / base may be non-NULL, both NULL = zeros.
  *   out  device packed operand array of out_alloc elements, element (c, p) at index out_off + c * out_stride + p
  *        (out_off % 8 == 0) */
 int svit_aggregate_split(const float* deltas, int64_t delta_stride, const float* w0, const float* base,

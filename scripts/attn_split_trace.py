@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Phase timeline of the split-precision tcgen05 attention kernel (CTA 0, first items), in SM cycles."""
+"""Phase timeline of the split-precision tcgen05 attention kernel (CTA 0, first items), in SM cycles.
+Needs a library whose attention_tc_split.cu was compiled with -DSVIT_ATT_TRACE (the instrumentation costs 20 % and is
+compiled out by default):  nvcc ... -DSVIT_ATT_TRACE -c attention_tc_split.cu, relink, SVIT_LIB=<that .so>."""
 import ctypes as C, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """BASELINE config 5: aggregation-only bandwidth sweep.  4-64 clients x ViT-S/B/L parameter stacks x coalition
-batch 1-128, 16-bit (operand feed) and fp32 (exact) outputs; achieved GB/s = algorithmic bytes / CUDA-event time,
-against the measured copy peak (MEASURED_PEAKS.json).   python scripts/k1_sweep.py > profiles/r1_k1_sweep.md"""
+batch 1-128, fp16, C8 (the default precision's operand feed) and fp32 (exact) outputs; achieved GB/s = algorithmic bytes / CUDA-event time,
+against the measured copy peak (MEASURED_PEAKS.json).   python scripts/k1_sweep.py > profiles/r2_k1_sweep.md"""
 import json
 import os
 import sys
@@ -46,23 +46,28 @@ for model, P in SIZES.items():
         torch.manual_seed(N)
         deltas = torch.randn(N, stride, device="cuda") * 0.02
         w0 = torch.randn(stride, device="cuda") * 0.02
-        for dt in (torch.float16, torch.float32):
-            es = 2 if dt == torch.float16 else 4
+        for kind in ("f16", "c8", "f32"):
+            dt = torch.float32 if kind == "f32" else torch.float16
+            es = 2 if kind == "f16" else 4
             cells = []
             for Cn in (1, 2, 4, 8, 16, 32, 64, 128):
-                if Cn * stride * es + (N + 1) * stride * 4 > 150e9 or (dt == torch.float32 and Cn > 32):
+                if Cn * stride * es + (N + 1) * stride * 4 > 150e9 or (kind == "f32" and Cn > 32):
                     cells.append("—")
                     continue
                 masks = torch.rand(Cn, N) < 0.5
                 masks[:, 0] |= ~masks.any(dim=1)
                 n = torch.arange(1, N + 1, dtype=torch.float64) * 1000
                 ratios = (masks * n / (masks * n).sum(dim=1, keepdim=True)).float()
-                out = torch.empty(Cn, stride, dtype=dt, device="cuda")
+                if kind == "c8":   # the default precision's operand feed: fp16 + two e4m3 planes, 4 bytes per element
+                    from shapley_vit_b200 import _lib
+                    out = ops.OperandArray((Cn, stride), torch.float16, _lib.FMT_C8, "cuda")
+                else:
+                    out = torch.empty(Cn, stride, dtype=dt, device="cuda")
                 ms = timeit(lambda: ops.aggregate(deltas, w0, ratios, out=out, P=P))
                 by = 4.0 * P * (N + 1) + es * P * Cn
                 gbs = by / ms / 1e6
                 cells.append(f"{gbs:.0f} ({gbs / peak:.2f})")
                 del out
-            print(f"| {N} | {'f16' if es == 2 else 'f32'} | " + " | ".join(cells) + " |", flush=True)
+            print(f"| {N} | {kind} | " + " | ".join(cells) + " |", flush=True)
         del deltas, w0
     print()
