@@ -57,10 +57,26 @@ def is_current() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile and link; safe under several processes at once (one rank per GPU all importing the package): an
+    exclusive file lock serialises the builders, the late comers find the library current, and the link goes to a
+    temporary name that is renamed into place, so no process ever maps a half-written file."""
     if not force and is_current():
         return LIB
-    nvcc = _nvcc()
+    import fcntl
+
     os.makedirs(OBJDIR, exist_ok=True)
+    with open(os.path.join(CSRC, ".libsvit.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():      # another process built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
+    nvcc = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
 
     def compile_one(src: str) -> str:
@@ -75,13 +91,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = f"{LIB}.tmp.{os.getpid()}"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link of libsvit.so failed")
-    with open(STAMP, "w") as f:
+    os.replace(tmp, LIB)                         # atomic: readers see the old or the new file, never a partial one
+    with open(STAMP + ".tmp", "w") as f:
         f.write(_fingerprint())
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 
