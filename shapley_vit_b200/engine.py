@@ -44,18 +44,27 @@ class ValidationSet:
             self.upload(images, labels, helper)
             helper.close()
 
-    def upload(self, images: torch.Tensor, labels: torch.Tensor, plan=None) -> int:
-        """(Re-)upload host images/labels; returns the bytes copied host -> device."""
+    UPLOAD_STEP = 1024   # images per host -> device copy + patchify launch
+
+    def upload(self, images: torch.Tensor, labels: torch.Tensor, plan=None, events: Optional[list] = None) -> int:
+        """(Re-)upload host images/labels; returns the bytes copied host -> device.  ``events``: a list that receives
+        one CUDA event per UPLOAD_STEP images (recorded on the current stream after their patch rows are written), so a
+        consumer on another stream can start on the first images while the rest is still in flight
+        (``CoalitionEngine.chunk_ready``)."""
         cfg = self.cfg
         own = plan is None
         with torch.cuda.device(self.device):
             if own:
                 plan = ops.Plan(cfg, self.precision, 1, 1, self.device)
-            step = 1024
+            step = self.UPLOAD_STEP
+            self.labels = labels.to(self.device, dtype=torch.int64, non_blocking=True).contiguous()
             for s in range(0, self.n, step):
                 img = images[s:s + step].to(self.device, dtype=torch.float32, non_blocking=True)
                 plan.patchify(img, out=self.patches, row0=s * cfg.n_patches)
-            self.labels = labels.to(self.device, dtype=torch.int64, non_blocking=True).contiguous()
+                if events is not None:
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    events.append(ev)
             if own:
                 torch.cuda.current_stream().synchronize()
                 plan.close()
@@ -104,6 +113,7 @@ class CoalitionEngine:
         self.last_logits: Optional[torch.Tensor] = None
         self.kernel_launches = 0
         self.profile = False                      # bench.py: CUDA-event pairs around the K1 launches
+        self.chunk_ready = None                   # optional callable(lo, hi) run before the forward of images [lo, hi)
         self.agg_spans: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
         self.round_deltas: List[torch.Tensor] = []   # multi-round mode (set_round_deltas)
         self._partial: Optional[torch.Tensor] = None
@@ -196,6 +206,8 @@ class CoalitionEngine:
         lo, hi = image_range if image_range is not None else (0, self.n_val)
         for s in range(lo, hi, self.image_chunk):
             b = min(self.image_chunk, hi - s)
+            if self.chunk_ready is not None:
+                self.chunk_ready(s, s + b)        # e.g. wait for the upload events covering these images
             self._forward(Cn, s * npch, b, logits, s)
         self.kernel_launches += 2 + ((hi - lo + self.image_chunk - 1) // self.image_chunk) * (3 + 7 * cfg.layers) + 1
         if records is not None:
