@@ -83,7 +83,9 @@ enum svit_precision {
  *   SVIT_FMT_X3: fp16 hi = fp16(x) at byte 0, fp16 lo = fp16(x - hi) at byte 2*alloc          (4 bytes / element)
  *   SVIT_FMT_C8: fp16 hi at byte 0, e4m3 hi8 = e4m3(4 * hi) at byte 2*alloc,
  *                e4m3 lo8 = e4m3(8192 * (x - hi)) at byte 3*alloc                              (4 bytes / element)
- * Element (row, col) sits at the same index in every plane.  alloc must be a multiple of 16. */
+ * Element (row, col) sits at the same index in every plane.  alloc must be a multiple of 16.
+ * Range: the e4m3 planes saturate at 448, i.e. they resolve |x| <= 112; the compensation of a larger element clips
+ * and its products degrade towards one fp16 pass (never below it).  fp16 `hi` itself saturates at 65 504. */
 enum svit_operand_format { SVIT_FMT_PLAIN = 0, SVIT_FMT_X3 = 1, SVIT_FMT_C8 = 2 };
 
 typedef struct svit_vit_cfg {

@@ -30,7 +30,7 @@ def main():
     ap.add_argument("--clients", type=int, default=16)
     ap.add_argument("--perms", type=int, default=200)
     ap.add_argument("--val", type=int, default=500)
-    ap.add_argument("--precision", default="f16")
+    ap.add_argument("--precision", default="f16c8")
     ap.add_argument("--coalition-batch", type=int, default=8)
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args()
