@@ -481,14 +481,15 @@ def test_gemm_k_extension_and_shared_b(ops, prec_name, tol, shape):
 def test_gemm_f16c8_outlier_operands_degrade_gracefully(ops):
     """The e4m3 planes resolve |x| <= 112 (hi8 = e4m3(4 hi) and lo8 = e4m3(8192 lo) saturate at 448); beyond that the
     compensation of an element clips and its product falls back towards ONE fp16 pass -- never worse (VERDICT r1, weak
-    10: outlier channels of pretrained ViTs).  A with a few channels x 300 and a row x 1000."""
+    10: outlier channels of pretrained ViTs).  A with two channels x 300 and a row x 30 (everything inside fp16's range)."""
     from shapley_vit_b200._lib import PRECISIONS
 
     G, M, N, K = 2, 300, 512, 768
     A, B = gen(G, M, K, seed=41), gen(G, N, K, seed=42) * 0.05
     A[:, :, 5] *= 300.0
     A[:, :, 300] *= 300.0
-    A[:, 7, :] *= 1000.0
+    A[:, 7, :] *= 30.0
+    assert float(A.abs().max()) < 65504
     want = ref_gemm(A, B)
     one_pass = (ref_gemm(A.half().float(), B.half().float()) - want).abs()
     got = ops.gemm(PRECISIONS["f16c8"], A.cuda(), B.cuda(), out_dtype=torch.float32).cpu().double()
@@ -498,5 +499,5 @@ def test_gemm_f16c8_outlier_operands_degrade_gracefully(ops):
     assert float((err / scale).max()) <= 1.05 * float((one_pass / scale).max()) + 1e-6
     inliers = torch.ones(M, dtype=torch.bool)
     inliers[7] = False
-    # rows without the x 1000 row still gain from the compensation of their in-range elements
+    # rows other than the x 30 row still gain from the compensation of their in-range elements
     assert float((err[:, inliers] / scale[:, inliers]).max()) < float((one_pass[:, inliers] / scale[:, inliers]).max())
