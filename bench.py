@@ -470,8 +470,9 @@ def run_ours(a):
             layout.pack_state_dict(lay, {k: cj[k] - w0_sd[k] for k in cj}, out=row)   # F1: delta_j = W_j - W_0
             deltas[j].copy_(row)
         del w0_sd
-    dist.broadcast_(deltas)
-    dist.broadcast_(w0)
+    if not a.lora_rank:                      # (LoRA line: every rank builds the same seeded PEFT state_dicts below)
+        dist.broadcast_(deltas)
+        dist.broadcast_(w0)
 
     # ---- validation set: replicated (same seed on every rank), host copy kept for the e2e leg --
     g = torch.Generator(device=dev).manual_seed(a.seed + 424243)
