@@ -129,16 +129,35 @@ def test_main_shapley_reads_client_checkpoints_and_waits_for_a_late_one(tmp_path
         target = final if j < 2 else d / "ViT_epoch_9.pth.tar.writing"      # the third one is still being written
         torch.save({"state_dict": {f"module.{k}": v for k, v in sd.items()}, "epoch": 9}, target)
         finals.append((target, final))
-    release = threading.Timer(4.0, lambda: os.replace(*finals[2]))
-    release.start()
     flags = ["--synthetic_data", "--vit_size", "tiny", "--image_size", "32", "--num_classes", "10", "--val_size", "96",
              "--num_clients", "3", "--dtype", "f32", "--seed", "3", "--approximation_method", "exact",
              "-loadModel", str(init_path), "--exp_dir", str(tmp_path)]
+    # the writer releases the third checkpoint only once the reader has been seen waiting for it (event-driven, so the
+    # test does not depend on how long the interpreter takes to start on a cold box)
+    proc = subprocess.Popen([sys.executable, "-u", os.path.join(ROOT, "mainShapley.py"), *flags], stdout=subprocess.PIPE,
+                            stderr=subprocess.PIPE, text=True, cwd=str(tmp_path))
+    lines, released = [], []
+
+    def pump():
+        for ln in proc.stdout:
+            lines.append(ln)
+            if "Waiting for the file to be unlocked..." in ln and not released:
+                released.append(True)
+                os.replace(*finals[2])
+
+    err = []
+    t_out, t_err = threading.Thread(target=pump), threading.Thread(target=lambda: err.append(proc.stderr.read()))
+    t_out.start(), t_err.start()
     try:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, "mainShapley.py"), *flags], capture_output=True, text=True,
-                             cwd=str(tmp_path), timeout=600)
+        rc = proc.wait(timeout=600)
     finally:
-        release.cancel()
+        if proc.poll() is None:
+            proc.kill()
+        t_out.join(), t_err.join()
+
+    import types
+
+    out = types.SimpleNamespace(returncode=rc, stdout="".join(lines), stderr="".join(err))
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("Waiting for the file to be unlocked...") >= 1
     assert out.stdout.count("Model loaded!") == 3
